@@ -1,0 +1,60 @@
+"""In-tree nvcc build of rsrl_b200/csrc/librsrl_b200.so for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(CSRC, "librsrl_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr"]
+HEADERS = ["device.cuh", "kernels.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
+
+
+def _units():
+    units = [("abi.o", "abi.cu", [])]
+    for rname, rtype in (("f32", "float"), ("f64", "double")):
+        for dom in (0, 1, 2):
+            suffix = f"{rname}_d{dom}"
+            units.append((f"inst_{suffix}.o", "inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"]))
+    return units
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    jobs = []
+    for obj, src, defs in _units():
+        o, s = os.path.join(OBJ, obj), os.path.join(CSRC, src)
+        if force or _stale(o, [s] + hdrs):
+            jobs.append([NVCC] + FLAGS + defs + ["-c", s, "-o", o])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        return r
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(run, jobs))
+    objs = [os.path.join(OBJ, u[0]) for u in _units()]
+    if jobs or _stale(LIB, objs):
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

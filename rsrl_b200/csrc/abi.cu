@@ -1,0 +1,845 @@
+// abi.cu — the C ABI of include/rsrl_b200.h: engine lifecycle, host<->device marshalling, dispatch.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+using namespace rsrl;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? RSRL_ENOMEM : RSRL_ECUDA,                          \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                                 \
+    } while (0)
+
+static int need_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RSRL_ENODEVICE, "no CUDA device visible: rsrl_b200 has no CPU fallback");
+    }
+    return RSRL_OK;
+}
+
+struct DevBuf {  // RAII device allocation for the stateless entry points
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------
+// config helpers
+// ---------------------------------------------------------------------------
+static int dom_dim(int d) { return d == RSRL_MOUNTAIN_CAR ? 2 : 4; }
+static int dom_actions(int d) { return d == RSRL_CART_POLE ? 2 : 3; }
+static bool algo_td_pred(int a) { return a == RSRL_TD_LAMBDA || a == RSRL_TD0; }
+static int64_t ipow(int64_t b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
+
+static int validate(const rsrl_config_t* c) {
+    if (!c) return fail(RSRL_EINVAL, "null config");
+    if (c->struct_size != sizeof(rsrl_config_t)) return fail(RSRL_EINVAL, "rsrl_config_t.struct_size mismatch (ABI)");
+    if (c->domain < 0 || c->domain > 2) return fail(RSRL_EINVAL, "unknown domain");
+    if (c->basis < 0 || c->basis > 2) return fail(RSRL_EINVAL, "unknown basis");
+    if (c->algo < 0 || c->algo > RSRL_TD0) return fail(RSRL_EINVAL, "unknown algo");
+    if (c->policy < 0 || c->policy > 2) return fail(RSRL_EINVAL, "unknown policy");
+    if (c->dtype != RSRL_F32 && c->dtype != RSRL_F64) return fail(RSRL_EINVAL, "unknown dtype");
+    if (c->weight_mode != RSRL_SHARED && c->weight_mode != RSRL_PER_ENV) return fail(RSRL_EINVAL, "unknown weight_mode");
+    if (c->n_envs <= 0) return fail(RSRL_EINVAL, "n_envs must be > 0");
+    if (c->env_offset < 0 || c->env_offset + c->n_envs > 0xFFFFFFFFll) return fail(RSRL_EINVAL, "global env ids must fit 32 bits");
+    if (!(c->epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
+    if (c->basis != RSRL_TILE_CODING && (c->basis_order < 1 || c->basis_order > 7)) return fail(RSRL_EINVAL, "basis_order must be in 1..7");
+    if (algo_td_pred(c->algo) && c->policy != RSRL_RANDOM)
+        return fail(RSRL_EINVAL, "TD(0)/TD(lambda) predict V(s): the behaviour policy must be RSRL_RANDOM");
+    return RSRL_OK;
+}
+
+static BasisKey key_of(const rsrl_config_t* c) {
+    BasisKey k;
+    k.dtype = c->dtype; k.domain = c->domain; k.basis = c->basis; k.order = c->basis_order;
+    k.aw = algo_td_pred(c->algo) ? 1 : dom_actions(c->domain);
+    return k;
+}
+
+static PolicyParams policy_of(int policy, double eps, uint64_t seed) {
+    PolicyParams p;
+    p.policy = policy;
+    p.eps_always = eps >= 1.0;
+    p.eps_thresh = p.eps_always ? 0xFFFFFFFFu : (uint32_t)(eps * 4294967296.0);
+    p.seed = seed;
+    return p;
+}
+
+static cudaError_t dispatch_fused(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    static const fused_launch_fn table[2][3] = {{launch_fused_f32_d0, launch_fused_f32_d1, launch_fused_f32_d2},
+                                                {launch_fused_f64_d0, launch_fused_f64_d1, launch_fused_f64_d2}};
+    return table[k.dtype][k.domain](k, mode, ext, a, grid, block, smem, st);
+}
+static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStream_t st) {
+    static const eval_launch_fn table[2][3] = {{launch_eval_f32_d0, launch_eval_f32_d1, launch_eval_f32_d2},
+                                               {launch_eval_f64_d0, launch_eval_f64_d1, launch_eval_f64_d2}};
+    return table[k.dtype][k.domain](k, e, st);
+}
+
+static int unsupported(const rsrl_config_t* c) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "combination not built: domain=%d basis=%d order=%d dtype=%d (see DESIGN.md)", c->domain, c->basis, c->basis_order, c->dtype);
+    return fail(RSRL_EUNSUPPORTED, buf);
+}
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen (only needed for multi-GPU SHARED mode)
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.h) return RSRL_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(RSRL_ECOMM, std::string("dlopen libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(RSRL_ECOMM, "libnccl.so.2 lacks a required symbol");
+    g_nccl.h = h;
+    return RSRL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------
+struct rsrl_engine {
+    rsrl_config_t cfg;
+    BasisKey key;
+    int D = 0, A = 0, AW = 0;
+    int64_t N = 0, NG = 0, F = 0, FA = 0;
+    bool has_trace = false;
+    size_t rsz = 4;
+    cudaStream_t stream = nullptr;
+    // device state
+    double* states = nullptr;
+    int32_t *actions = nullptr, *ep_steps = nullptr, *n_ep = nullptr, *last_len = nullptr;
+    unsigned long long* len_hash = nullptr;
+    void *td = nullptr, *W = nullptr, *z = nullptr, *partials = nullptr, *dW = nullptr;
+    Counters* counters = nullptr;
+    double* stage = nullptr;  // f64 staging for import/export
+    size_t stage_elems = 0;
+    double* init_bounds = nullptr;  // lo[4], hi[4]
+    // launch shape
+    int grid = 0, block = 0;
+    size_t smem = 0;
+    uint64_t t = 0;
+    int64_t launches = 0;
+    double epsilon = 0.0;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+static size_t wcount(const rsrl_engine* e) { return (size_t)e->FA * (e->cfg.weight_mode == RSRL_PER_ENV ? (size_t)e->N : 1); }
+
+static int ensure_stage(rsrl_engine* e, size_t elems) {
+    if (elems <= e->stage_elems) return RSRL_OK;
+    if (e->stage) cudaFree(e->stage);
+    e->stage = nullptr; e->stage_elems = 0;
+    CU_TRY(cudaMalloc(&e->stage, elems * sizeof(double)));
+    e->stage_elems = elems;
+    return RSRL_OK;
+}
+
+static void choose_launch(rsrl_engine* e) {
+    if (e->cfg.weight_mode == RSRL_PER_ENV) {
+        e->block = 128; e->smem = 0;
+    } else {
+        const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;
+        int block = 256;
+        for (;; block /= 2) {
+            const size_t bytes = (((size_t)e->FA + 3) & ~(size_t)3) * e->rsz + rows * block * e->rsz + (size_t)(e->has_trace ? 1 : e->AW) * block * e->rsz;
+            e->smem = bytes;
+            if (bytes <= 200 * 1024 || block == 32) break;
+        }
+        e->block = block;
+    }
+    e->grid = (int)((e->N + e->block - 1) / e->block);
+}
+
+static StepArgs make_args(rsrl_engine* e) {
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.states = e->states; a.actions = e->actions; a.ep_steps = e->ep_steps; a.n_ep = e->n_ep; a.last_len = e->last_len;
+    a.len_hash = e->len_hash; a.td = e->td; a.W = e->W; a.z = e->z; a.partials = e->partials; a.counters = e->counters;
+    a.n = e->N; a.env_offset = e->cfg.env_offset; a.t = e->t; a.max_ep = e->cfg.max_episode_steps;
+    a.algo = e->cfg.algo; a.trace_rule = e->cfg.trace_rule; a.init_mode = e->cfg.init_mode;
+    a.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed);
+    const double scale = (e->cfg.weight_mode == RSRL_SHARED && e->cfg.update_scale == RSRL_SCALE_MEAN) ? (double)e->NG : 1.0;
+    a.gamma = e->cfg.gamma; a.lr_scaled = e->cfg.lr / scale; a.alpha = e->cfg.alpha; a.inv_scale = 1.0 / scale;
+    a.lambda = e->cfg.lambda; a.epsilon = e->epsilon;
+    for (int d = 0; d < RSRL_MAX_DIM; ++d) { a.init_lo[d] = e->cfg.init_lo[d]; a.init_hi[d] = e->cfg.init_hi[d]; }
+    return a;
+}
+
+template <typename R>
+static cudaError_t launch_reduce(rsrl_engine* e, int n_blocks) {
+    const int threads = 128, blocks = (int)((e->FA + threads - 1) / threads);
+    reduce_partials_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<const R*>(e->partials), n_blocks, (int)e->FA,
+                                                                  static_cast<R*>(e->W), e->world > 1 ? static_cast<R*>(e->dW) : nullptr);
+    return cudaGetLastError();
+}
+template <typename R>
+static cudaError_t launch_add(rsrl_engine* e) {
+    const int threads = 128, blocks = (int)((e->FA + threads - 1) / threads);
+    add_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<R*>(e->W), static_cast<const R*>(e->dW), (int)e->FA);
+    return cudaGetLastError();
+}
+
+// after a SHARED-mode fused launch: partials -> dW (-> allreduce) -> W
+static int finish_shared_step(rsrl_engine* e, int n_blocks) {
+    CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks) : launch_reduce<double>(e, n_blocks));
+    e->launches += 1;
+    if (e->world > 1) {
+        ncclResult_t r = g_nccl.AllReduce(e->dW, e->dW, (size_t)e->FA, e->cfg.dtype == RSRL_F32 ? ncclFloat32 : ncclFloat64,
+                                          ncclSum, e->comm, e->stream);
+        if (r != ncclSuccess) return fail(RSRL_ECOMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+        CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_add<float>(e) : launch_add<double>(e));
+        e->launches += 1;
+    }
+    return RSRL_OK;
+}
+
+extern "C" {
+
+int rsrl_version(void) { return RSRL_ABI_VERSION; }
+const char* rsrl_last_error(void) { return g_err.c_str(); }
+
+int rsrl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rsrl_config_default(rsrl_config_t* c) {
+    if (!c) return fail(RSRL_EINVAL, "null config");
+    memset(c, 0, sizeof *c);
+    c->struct_size = sizeof *c;
+    c->domain = RSRL_MOUNTAIN_CAR; c->basis = RSRL_FOURIER; c->basis_order = 5;
+    c->n_tilings = 8; c->tiles_per_dim = 8; c->memory_size = 4096;
+    c->algo = RSRL_QLEARNING; c->policy = RSRL_GREEDY; c->trace_rule = RSRL_TRACE_REPLACE;
+    c->weight_mode = RSRL_SHARED; c->update_scale = RSRL_SCALE_SUM; c->dtype = RSRL_F32; c->init_mode = RSRL_INIT_DEFAULT;
+    c->n_envs = 1;
+    c->lr = 0.001; c->alpha = 0.01; c->gamma = 0.9; c->lambda = 0.7; c->epsilon = 0.1;
+    return RSRL_OK;
+}
+
+int rsrl_config_dims(const rsrl_config_t* c, int32_t* dim, int32_t* n_actions, int64_t* n_features) {
+    int rc = validate(c);
+    if (rc) return rc;
+    if (dim) *dim = dom_dim(c->domain);
+    if (n_actions) *n_actions = dom_actions(c->domain);
+    if (n_features) *n_features = c->basis == RSRL_TILE_CODING ? c->memory_size : ipow(c->basis_order + 1, dom_dim(c->domain));
+    return RSRL_OK;
+}
+
+int rsrl_engine_destroy(rsrl_engine_t* e) {
+    if (!e) return RSRL_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return RSRL_OK;
+}
+
+int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
+    if (!out) return fail(RSRL_EINVAL, "null out");
+    *out = nullptr;
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if ((rc = need_device())) return rc;
+    if (cfg->basis == RSRL_TILE_CODING) return unsupported(cfg);
+    CU_TRY(cudaSetDevice(cfg->device));
+    rsrl_engine* e = new rsrl_engine();
+    e->cfg = *cfg;
+    e->key = key_of(cfg);
+    e->D = dom_dim(cfg->domain); e->A = dom_actions(cfg->domain); e->AW = e->key.aw;
+    e->N = cfg->n_envs; e->NG = cfg->n_envs_global > 0 ? cfg->n_envs_global : cfg->n_envs;
+    e->F = ipow(cfg->basis_order + 1, e->D); e->FA = e->F * e->AW;
+    e->has_trace = algo_has_trace(cfg->algo);
+    e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
+    e->epsilon = cfg->epsilon;
+    choose_launch(e);
+#define E_TRY(expr)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            rsrl_engine_destroy(e);                                                                  \
+            return fail(e__ == cudaErrorMemoryAllocation ? RSRL_ENOMEM : RSRL_ECUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
+        }                                                                                            \
+    } while (0)
+    E_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t N = (size_t)e->N;
+    E_TRY(cudaMalloc(&e->states, N * e->D * sizeof(double)));
+    E_TRY(cudaMalloc(&e->actions, N * sizeof(int32_t)));
+    E_TRY(cudaMalloc(&e->ep_steps, N * sizeof(int32_t)));
+    E_TRY(cudaMalloc(&e->n_ep, N * sizeof(int32_t)));
+    E_TRY(cudaMalloc(&e->last_len, N * sizeof(int32_t)));
+    E_TRY(cudaMalloc(&e->len_hash, N * sizeof(unsigned long long)));
+    if (cfg->record_td_error) E_TRY(cudaMalloc(&e->td, N * e->rsz));
+    E_TRY(cudaMalloc(&e->W, wcount(e) * e->rsz));
+    if (e->has_trace) E_TRY(cudaMalloc(&e->z, (size_t)e->FA * N * e->rsz));
+    if (cfg->weight_mode == RSRL_SHARED) {
+        E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
+        E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
+    }
+    E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
+    E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
+    // probe that the combination is built (fails loudly instead of at the first step)
+    {
+        StepArgs a = make_args(e);
+        a.n = 0;
+        cudaError_t pe = dispatch_fused(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream);
+        if (pe == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); rsrl_engine_destroy(e); return unsupported(cfg); }
+        E_TRY(pe);
+        E_TRY(cudaStreamSynchronize(e->stream));
+    }
+#undef E_TRY
+    rc = rsrl_engine_reset(e, nullptr);
+    if (rc) { rsrl_engine_destroy(e); return rc; }
+    *out = e;
+    return RSRL_OK;
+}
+
+int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
+    if (!e) return fail(RSRL_EINVAL, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t N = (size_t)e->N;
+    cudaStream_t st = e->stream;
+    CU_TRY(cudaMemsetAsync(e->W, 0, wcount(e) * e->rsz, st));  // LFA::vector => Array2::zeros (examples/q_learning.rs:25)
+    if (e->z) CU_TRY(cudaMemsetAsync(e->z, 0, (size_t)e->FA * N * e->rsz, st));
+    if (e->td) CU_TRY(cudaMemsetAsync(e->td, 0, N * e->rsz, st));
+    CU_TRY(cudaMemsetAsync(e->actions, 0xFF, N * sizeof(int32_t), st));  // -1
+    CU_TRY(cudaMemsetAsync(e->ep_steps, 0, N * sizeof(int32_t), st));
+    CU_TRY(cudaMemsetAsync(e->n_ep, 0, N * sizeof(int32_t), st));
+    CU_TRY(cudaMemsetAsync(e->last_len, 0, N * sizeof(int32_t), st));
+    CU_TRY(cudaMemsetAsync(e->len_hash, 0, N * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(e->counters, 0, sizeof(Counters), st));
+    e->t = 0;
+    if (init_states) {
+        CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        double b[8];
+        for (int d = 0; d < 4; ++d) { b[d] = e->cfg.init_lo[d]; b[4 + d] = e->cfg.init_hi[d]; }
+        CU_TRY(cudaMemcpyAsync(e->init_bounds, b, sizeof b, cudaMemcpyHostToDevice, st));
+        const int threads = 128, blocks = (int)((e->N + threads - 1) / threads);
+        if (e->cfg.domain == RSRL_MOUNTAIN_CAR)
+            init_states_kernel<RSRL_MOUNTAIN_CAR><<<blocks, threads, 0, st>>>(e->N, e->states, e->cfg.init_mode, e->init_bounds, e->init_bounds + 4, e->cfg.seed, e->cfg.env_offset);
+        else if (e->cfg.domain == RSRL_CART_POLE)
+            init_states_kernel<RSRL_CART_POLE><<<blocks, threads, 0, st>>>(e->N, e->states, e->cfg.init_mode, e->init_bounds, e->init_bounds + 4, e->cfg.seed, e->cfg.env_offset);
+        else
+            init_states_kernel<RSRL_ACROBOT><<<blocks, threads, 0, st>>>(e->N, e->states, e->cfg.init_mode, e->init_bounds, e->init_bounds + 4, e->cfg.seed, e->cfg.env_offset);
+        CU_TRY(cudaGetLastError());
+        e->launches += 1;
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    return RSRL_OK;
+}
+
+int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
+    if (!e) return fail(RSRL_EINVAL, "null engine");
+    if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    for (int64_t k = 0; k < k_steps; ++k) {
+        StepArgs a = make_args(e);
+        CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream));
+        e->launches += 1;
+        if (e->cfg.weight_mode == RSRL_SHARED) {
+            int rc = finish_shared_step(e, e->grid);
+            if (rc) return rc;
+        }
+        e->t += 1;
+    }
+    return RSRL_OK;
+}
+
+int rsrl_engine_sync(rsrl_engine_t* e) {
+    if (!e) return fail(RSRL_EINVAL, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    Counters c;
+    CU_TRY(cudaMemcpy(&c, e->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum (NaN weights); the reference panics in utils.rs:76");
+    return RSRL_OK;
+}
+
+void* rsrl_engine_stream(rsrl_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+
+#define GET_SIMPLE(name, field, type)                                                                         \
+    int name(rsrl_engine_t* e, type* out) {                                                                   \
+        if (!e || !out) return fail(RSRL_EINVAL, "null argument");                                            \
+        CU_TRY(cudaSetDevice(e->cfg.device));                                                                 \
+        CU_TRY(cudaMemcpyAsync(out, e->field, (size_t)e->N * sizeof(type), cudaMemcpyDeviceToHost, e->stream)); \
+        CU_TRY(cudaStreamSynchronize(e->stream));                                                             \
+        return RSRL_OK;                                                                                       \
+    }
+GET_SIMPLE(rsrl_engine_get_actions, actions, int32_t)
+GET_SIMPLE(rsrl_engine_get_episode_steps, ep_steps, int32_t)
+
+int rsrl_engine_get_states(rsrl_engine_t* e, double* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaMemcpyAsync(out, e->states, (size_t)e->N * e->D * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+int rsrl_engine_set_states(rsrl_engine_t* e, const double* in) {
+    if (!e || !in) return fail(RSRL_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaMemcpyAsync(e->states, in, (size_t)e->N * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+static int export_tensor(rsrl_engine* e, const void* src, int64_t n_env, int64_t fa, int transposed, double* out) {
+    const size_t elems = (size_t)n_env * fa;
+    int rc = ensure_stage(e, elems);
+    if (rc) return rc;
+    const int threads = 256, blocks = (int)((elems + threads - 1) / threads);
+    if (e->cfg.dtype == RSRL_F32) export_kernel<float><<<blocks, threads, 0, e->stream>>>(static_cast<const float*>(src), e->stage, n_env, fa, transposed);
+    else export_kernel<double><<<blocks, threads, 0, e->stream>>>(static_cast<const double*>(src), e->stage, n_env, fa, transposed);
+    CU_TRY(cudaGetLastError());
+    e->launches += 1;
+    CU_TRY(cudaMemcpyAsync(out, e->stage, elems * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+static int import_tensor(rsrl_engine* e, void* dst, int64_t n_env, int64_t fa, int transposed, const double* in) {
+    const size_t elems = (size_t)n_env * fa;
+    int rc = ensure_stage(e, elems);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(e->stage, in, elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    const int threads = 256, blocks = (int)((elems + threads - 1) / threads);
+    if (e->cfg.dtype == RSRL_F32) import_kernel<float><<<blocks, threads, 0, e->stream>>>(e->stage, static_cast<float*>(dst), n_env, fa, transposed);
+    else import_kernel<double><<<blocks, threads, 0, e->stream>>>(e->stage, static_cast<double*>(dst), n_env, fa, transposed);
+    CU_TRY(cudaGetLastError());
+    e->launches += 1;
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+int rsrl_engine_get_weights(rsrl_engine_t* e, double* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    return export_tensor(e, e->W, pe ? e->N : 1, e->FA, pe, out);
+}
+int rsrl_engine_set_weights(rsrl_engine_t* e, const double* in) {
+    if (!e || !in) return fail(RSRL_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    return import_tensor(e, e->W, pe ? e->N : 1, e->FA, pe, in);
+}
+int rsrl_engine_get_traces(rsrl_engine_t* e, double* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    if (!e->z) return fail(RSRL_EINVAL, "the configured algorithm has no eligibility trace");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    return export_tensor(e, e->z, e->N, e->FA, 1, out);
+}
+int rsrl_engine_set_traces(rsrl_engine_t* e, const double* in) {
+    if (!e || !in) return fail(RSRL_EINVAL, "null argument");
+    if (!e->z) return fail(RSRL_EINVAL, "the configured algorithm has no eligibility trace");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    return import_tensor(e, e->z, e->N, e->FA, 1, in);
+}
+int rsrl_engine_get_td_errors(rsrl_engine_t* e, double* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    if (!e->td) return fail(RSRL_EINVAL, "engine was created with record_td_error = 0");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    return export_tensor(e, e->td, 1, e->N, 0, out);
+}
+
+int rsrl_engine_get_stats(rsrl_engine_t* e, rsrl_stats_t* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    Counters c;
+    CU_TRY(cudaMemcpy(&c, e->counters, sizeof c, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->total_steps = (int64_t)e->t * e->N;
+    out->total_episodes = (int64_t)c.episodes;
+    out->terminal_episodes = (int64_t)c.terminal_episodes;
+    out->batch_steps = (int64_t)e->t;
+    out->kernel_launches = e->launches;
+    out->nonfinite = c.nonfinite;
+    return RSRL_OK;
+}
+
+int rsrl_engine_get_env_stats(rsrl_engine_t* e, int32_t* n_episodes, int32_t* last_len, uint64_t* len_hash) {
+    if (!e) return fail(RSRL_EINVAL, "null engine");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const size_t N = (size_t)e->N;
+    if (n_episodes) CU_TRY(cudaMemcpyAsync(n_episodes, e->n_ep, N * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (last_len) CU_TRY(cudaMemcpyAsync(last_len, e->last_len, N * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (len_hash) CU_TRY(cudaMemcpyAsync(len_hash, e->len_hash, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+int rsrl_engine_set_epsilon(rsrl_engine_t* e, double epsilon) {
+    if (!e) return fail(RSRL_EINVAL, "null engine");
+    if (!(epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
+    e->epsilon = epsilon;
+    return RSRL_OK;
+}
+
+// ---- trait-level entry points on the engine's weights ----
+static int engine_eval(rsrl_engine* e, int mode, int64_t n, const double* states, uint64_t draw, double* q_out, int32_t* act_out) {
+    if (!e || !states || n <= 0) return fail(RSRL_EINVAL, "bad argument");
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    if (pe && n != e->N) return fail(RSRL_EINVAL, "PER_ENV weights: n must equal n_envs (state i is evaluated with agent i)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    DevBuf ds, dout;
+    CU_TRY(ds.alloc((size_t)n * e->D * sizeof(double)));
+    CU_TRY(dout.alloc(mode == 1 ? (size_t)n * e->AW * sizeof(double) : (size_t)n * sizeof(int32_t)));
+    CU_TRY(cudaMemcpyAsync(ds.p, states, (size_t)n * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    EvalArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = e->W; ea.w_env_stride = pe ? 1 : 0;
+    ea.out = mode == 1 ? dout.as<double>() : nullptr; ea.act_out = mode == 1 ? nullptr : dout.as<int32_t>();
+    ea.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed); ea.draw = draw; ea.env_offset = e->cfg.env_offset; ea.counters = e->counters;
+    CU_TRY(dispatch_eval(e->key, ea, e->stream));
+    e->launches += 1;
+    if (mode == 1) CU_TRY(cudaMemcpyAsync(q_out, dout.p, (size_t)n * e->AW * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    else CU_TRY(cudaMemcpyAsync(act_out, dout.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return RSRL_OK;
+}
+
+int rsrl_engine_evaluate(rsrl_engine_t* e, int64_t n, const double* states, double* q_out) {
+    if (!q_out) return fail(RSRL_EINVAL, "null q_out");
+    return engine_eval(e, 1, n, states, 0, q_out, nullptr);
+}
+int rsrl_engine_sample(rsrl_engine_t* e, int64_t n, const double* states, uint64_t draw, int32_t* actions_out) {
+    if (!actions_out) return fail(RSRL_EINVAL, "null actions_out");
+    if (e && algo_td_pred(e->cfg.algo)) return fail(RSRL_EINVAL, "TD prediction engines have no Q-based policy");
+    return engine_eval(e, 2, n, states, draw, nullptr, actions_out);
+}
+int rsrl_engine_mode(rsrl_engine_t* e, int64_t n, const double* states, int32_t* actions_out) {
+    if (!actions_out) return fail(RSRL_EINVAL, "null actions_out");
+    if (e && algo_td_pred(e->cfg.algo)) return fail(RSRL_EINVAL, "TD prediction engines have no Q-based policy");
+    return engine_eval(e, 3, n, states, 0, nullptr, actions_out);
+}
+
+int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, const int32_t* actions, const double* rewards,
+                       const double* to_states, const uint8_t* terminal, uint64_t draw, double* td_out) {
+    if (!e || !from_states || !actions || !rewards || !to_states || !terminal || n <= 0) return fail(RSRL_EINVAL, "bad argument");
+    if ((e->has_trace || e->cfg.weight_mode == RSRL_PER_ENV) && n != e->N)
+        return fail(RSRL_EINVAL, "per-env traces / weights: n must equal n_envs (transition i belongs to agent i)");
+    if (n > e->N) return fail(RSRL_EINVAL, "n exceeds n_envs");
+    for (int64_t i = 0; i < n; ++i)
+        if (actions[i] < 0 || actions[i] >= e->A) return fail(RSRL_EINVAL, "action out of range");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    DevBuf dfrom, dto, dact, drew, dterm, dtd;
+    const size_t sb = (size_t)n * e->D * sizeof(double);
+    CU_TRY(dfrom.alloc(sb)); CU_TRY(dto.alloc(sb)); CU_TRY(dact.alloc(n * sizeof(int32_t)));
+    CU_TRY(drew.alloc(n * sizeof(double))); CU_TRY(dterm.alloc(n)); CU_TRY(dtd.alloc(n * e->rsz));
+    cudaStream_t st = e->stream;
+    CU_TRY(cudaMemcpyAsync(dfrom.p, from_states, sb, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(dto.p, to_states, sb, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(dact.p, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(drew.p, rewards, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(dterm.p, terminal, n, cudaMemcpyHostToDevice, st));
+    StepArgs a = make_args(e);
+    a.n = n; a.t = draw; a.td = dtd.p;
+    a.ext_from = dfrom.as<double>(); a.ext_to = dto.as<double>(); a.ext_actions = dact.as<int32_t>();
+    a.ext_rewards = drew.as<double>(); a.ext_term = dterm.as<uint8_t>();
+    const int grid = (int)((n + e->block - 1) / e->block);
+    CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, true, a, grid, e->block, e->smem, st));
+    e->launches += 1;
+    if (e->cfg.weight_mode == RSRL_SHARED) {
+        int rc = finish_shared_step(e, grid);
+        if (rc) return rc;
+    }
+    if (td_out) {
+        int rc = ensure_stage(e, (size_t)n);
+        if (rc) return rc;
+        const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+        if (e->cfg.dtype == RSRL_F32) export_kernel<float><<<blocks, threads, 0, st>>>(dtd.as<float>(), e->stage, 1, n, 0);
+        else export_kernel<double><<<blocks, threads, 0, st>>>(dtd.as<double>(), e->stage, 1, n, 0);
+        CU_TRY(cudaGetLastError());
+        e->launches += 1;
+        CU_TRY(cudaMemcpyAsync(td_out, e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    return RSRL_OK;
+}
+
+// ---- multi-GPU ----
+int rsrl_comm_unique_id(uint8_t out[128]) {
+    if (!out) return fail(RSRL_EINVAL, "null out");
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(RSRL_ECOMM, "ncclGetUniqueId failed");
+    memcpy(out, &id, 128);
+    return RSRL_OK;
+}
+
+int rsrl_engine_comm_init(rsrl_engine_t* e, const uint8_t id_bytes[128], int rank, int world) {
+    if (!e || !id_bytes || world < 1 || rank < 0 || rank >= world) return fail(RSRL_EINVAL, "bad argument");
+    if (world == 1) { e->rank = 0; e->world = 1; return RSRL_OK; }
+    int rc = load_nccl();
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&e->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(RSRL_ECOMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    e->rank = rank; e->world = world;
+    return RSRL_OK;
+}
+
+// ---- stateless component entry points ----
+int rsrl_domain_info(int32_t domain, int32_t* dim, int32_t* n_actions, double* lo, double* hi, double* start) {
+    if (domain < 0 || domain > 2) return fail(RSRL_EINVAL, "unknown domain");
+    const int D = dom_dim(domain);
+    if (dim) *dim = D;
+    if (n_actions) *n_actions = dom_actions(domain);
+    for (int d = 0; d < D; ++d) {
+        double l, h, s;
+        if (domain == RSRL_MOUNTAIN_CAR) { l = Domain<RSRL_MOUNTAIN_CAR>::lo(d); h = Domain<RSRL_MOUNTAIN_CAR>::hi(d); s = Domain<RSRL_MOUNTAIN_CAR>::start(d); }
+        else if (domain == RSRL_CART_POLE) { l = Domain<RSRL_CART_POLE>::lo(d); h = Domain<RSRL_CART_POLE>::hi(d); s = Domain<RSRL_CART_POLE>::start(d); }
+        else { l = Domain<RSRL_ACROBOT>::lo(d); h = Domain<RSRL_ACROBOT>::hi(d); s = Domain<RSRL_ACROBOT>::start(d); }
+        if (lo) lo[d] = l;
+        if (hi) hi[d] = h;
+        if (start) start[d] = s;
+    }
+    return RSRL_OK;
+}
+
+static int domain_call(int32_t domain, int64_t n, double* states_inout, const double* states_in, const int32_t* actions,
+                       double* rewards_out, uint8_t* terminal_out) {
+    if (domain < 0 || domain > 2 || n <= 0 || !terminal_out) return fail(RSRL_EINVAL, "bad argument");
+    int rc = need_device();
+    if (rc) return rc;
+    const int D = dom_dim(domain);
+    if (actions) for (int64_t i = 0; i < n; ++i) if (actions[i] < 0 || actions[i] >= dom_actions(domain)) return fail(RSRL_EINVAL, "action out of range");
+    DevBuf ds, da, dr, dt;
+    const size_t sb = (size_t)n * D * sizeof(double);
+    CU_TRY(ds.alloc(sb)); CU_TRY(da.alloc(n * sizeof(int32_t))); CU_TRY(dr.alloc(n * sizeof(double))); CU_TRY(dt.alloc(n));
+    CU_TRY(cudaMemcpy(ds.p, actions ? states_inout : states_in, sb, cudaMemcpyHostToDevice));
+    if (actions) CU_TRY(cudaMemcpy(da.p, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    const int32_t* dact = actions ? da.as<int32_t>() : nullptr;
+    if (domain == RSRL_MOUNTAIN_CAR) domain_step_kernel<RSRL_MOUNTAIN_CAR><<<blocks, threads>>>(n, ds.as<double>(), dact, dr.as<double>(), dt.as<uint8_t>());
+    else if (domain == RSRL_CART_POLE) domain_step_kernel<RSRL_CART_POLE><<<blocks, threads>>>(n, ds.as<double>(), dact, dr.as<double>(), dt.as<uint8_t>());
+    else domain_step_kernel<RSRL_ACROBOT><<<blocks, threads>>>(n, ds.as<double>(), dact, dr.as<double>(), dt.as<uint8_t>());
+    CU_TRY(cudaGetLastError());
+    if (actions) {
+        CU_TRY(cudaMemcpy(states_inout, ds.p, sb, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(rewards_out, dr.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    CU_TRY(cudaMemcpy(terminal_out, dt.p, n, cudaMemcpyDeviceToHost));
+    return RSRL_OK;
+}
+
+int rsrl_domain_step(int32_t domain, int64_t n, double* states_inout, const int32_t* actions, double* rewards_out, uint8_t* terminal_out) {
+    if (!states_inout || !actions || !rewards_out) return fail(RSRL_EINVAL, "null argument");
+    return domain_call(domain, n, states_inout, nullptr, actions, rewards_out, terminal_out);
+}
+int rsrl_domain_is_terminal(int32_t domain, int64_t n, const double* states, uint8_t* terminal_out) {
+    if (!states) return fail(RSRL_EINVAL, "null argument");
+    return domain_call(domain, n, nullptr, states, nullptr, nullptr, terminal_out);
+}
+
+static int stateless_eval(const rsrl_config_t* cfg, int mode, int64_t n, const double* states, const double* weights, int aw, double* out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (n <= 0 || !states || !out) return fail(RSRL_EINVAL, "bad argument");
+    if ((rc = need_device())) return rc;
+    if (cfg->basis == RSRL_TILE_CODING) return unsupported(cfg);
+    BasisKey k = key_of(cfg);
+    k.aw = aw;
+    const int D = dom_dim(cfg->domain);
+    const int64_t F = ipow(cfg->basis_order + 1, D);
+    const size_t rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
+    const size_t out_elems = (size_t)n * (mode == 0 ? F : aw);
+    DevBuf ds, dw, dwr, dout;
+    CU_TRY(ds.alloc((size_t)n * D * sizeof(double))); CU_TRY(dout.alloc(out_elems * sizeof(double)));
+    CU_TRY(cudaMemcpy(ds.p, states, (size_t)n * D * sizeof(double), cudaMemcpyHostToDevice));
+    if (mode == 1) {
+        CU_TRY(dw.alloc((size_t)F * aw * sizeof(double))); CU_TRY(dwr.alloc((size_t)F * aw * rsz));
+        CU_TRY(cudaMemcpy(dw.p, weights, (size_t)F * aw * sizeof(double), cudaMemcpyHostToDevice));
+        const int threads = 256, blocks = (int)((F * aw + threads - 1) / threads);
+        if (cfg->dtype == RSRL_F32) import_kernel<float><<<blocks, threads>>>(dw.as<double>(), dwr.as<float>(), 1, F * aw, 0);
+        else import_kernel<double><<<blocks, threads>>>(dw.as<double>(), dwr.as<double>(), 1, F * aw, 0);
+        CU_TRY(cudaGetLastError());
+    }
+    EvalArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = dwr.p; ea.out = dout.as<double>();
+    cudaError_t ce = dispatch_eval(k, ea, 0);
+    if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(cfg); }
+    CU_TRY(ce);
+    CU_TRY(cudaMemcpy(out, dout.p, out_elems * sizeof(double), cudaMemcpyDeviceToHost));
+    return RSRL_OK;
+}
+
+int rsrl_basis_project(const rsrl_config_t* cfg, int64_t n, const double* states, double* features_out) {
+    return stateless_eval(cfg, 0, n, states, nullptr, cfg ? dom_actions(cfg->domain) : 0, features_out);
+}
+
+int rsrl_lfa_evaluate(const rsrl_config_t* cfg, int64_t n, const double* states, const double* weights, double* q_out) {
+    if (!weights) return fail(RSRL_EINVAL, "null weights");
+    return stateless_eval(cfg, 1, n, states, weights, cfg ? key_of(cfg).aw : 0, q_out);
+}
+
+int rsrl_lfa_update_index(const rsrl_config_t* cfg, int64_t n, const double* states, const int32_t* actions, const double* errors, double* weights_inout) {
+    // W[:, a_i] += (lr * err_i) * phi(s_i), summed over the batch: a SHARED/SUM Q-learning engine fed
+    // terminal transitions with reward = err and W = 0 for the TD part reproduces exactly that update.
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (n <= 0 || !states || !actions || !errors || !weights_inout) return fail(RSRL_EINVAL, "bad argument");
+    rsrl_config_t c = *cfg;
+    c.algo = RSRL_QLEARNING; c.weight_mode = RSRL_SHARED; c.update_scale = RSRL_SCALE_SUM; c.n_envs = n; c.n_envs_global = n;
+    c.record_td_error = 0; c.env_offset = 0;
+    rsrl_engine_t* e = nullptr;
+    if ((rc = rsrl_engine_create(&c, &e))) return rc;
+    // zero weights => qsa = 0 => delta = reward = err_i
+    std::vector<uint8_t> term((size_t)n, 1);
+    rc = rsrl_engine_handle(e, n, states, actions, errors, states, term.data(), 0, nullptr);
+    std::vector<double> dw((size_t)e->FA);
+    if (!rc) rc = rsrl_engine_get_weights(e, dw.data());
+    if (!rc) for (int64_t j = 0; j < e->FA; ++j) weights_inout[j] += dw[(size_t)j];
+    rsrl_engine_destroy(e);
+    return rc;
+}
+
+}  // extern "C"
+
+template <int A>
+static cudaError_t run_policy(int dtype, int mode, int64_t n, const double* dq, PolicyParams pol, double eps, uint64_t draw,
+                              int64_t env_offset, int32_t* act, double* probs, Counters* cnt) {
+    const int threads = 128, blocks = (int)((n + threads - 1) / threads);
+    if (dtype == RSRL_F32) policy_kernel<float, A><<<blocks, threads>>>(mode, n, dq, pol, eps, draw, env_offset, act, probs, cnt);
+    else policy_kernel<double, A><<<blocks, threads>>>(mode, n, dq, pol, eps, draw, env_offset, act, probs, cnt);
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+static int policy_call(int mode, int32_t policy, double eps, uint64_t seed, uint64_t draw, int64_t env_offset, int64_t n,
+                       int32_t A, const double* q, int32_t* act_out, double* probs_out) {
+    if (n <= 0 || !q || A < 1 || A > 8) return fail(RSRL_EINVAL, "bad argument (1 <= n_actions <= 8)");
+    if (policy < 0 || policy > 2 || !(eps >= 0.0)) return fail(RSRL_EINVAL, "bad policy / epsilon");
+    int rc = need_device();
+    if (rc) return rc;
+    DevBuf dq, dout, dc;
+    CU_TRY(dq.alloc((size_t)n * A * sizeof(double)));
+    CU_TRY(dout.alloc(mode == 1 ? (size_t)n * A * sizeof(double) : (size_t)n * sizeof(int32_t)));
+    CU_TRY(dc.alloc(sizeof(Counters)));
+    CU_TRY(cudaMemset(dc.p, 0, sizeof(Counters)));
+    CU_TRY(cudaMemcpy(dq.p, q, (size_t)n * A * sizeof(double), cudaMemcpyHostToDevice));
+    PolicyParams pol = policy_of(policy, eps, seed);
+    int32_t* da = mode == 1 ? nullptr : dout.as<int32_t>();
+    double* dp = mode == 1 ? dout.as<double>() : nullptr;
+    // explicit Q vectors are compared in f64: these entry points mirror the reference's f64 MockQ tests
+    cudaError_t ce;
+    switch (A) {
+        case 1: ce = run_policy<1>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 2: ce = run_policy<2>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 3: ce = run_policy<3>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 4: ce = run_policy<4>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 5: ce = run_policy<5>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 6: ce = run_policy<6>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        case 7: ce = run_policy<7>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+        default: ce = run_policy<8>(RSRL_F64, mode, n, dq.as<double>(), pol, eps, draw, env_offset, da, dp, dc.as<Counters>()); break;
+    }
+    CU_TRY(ce);
+    if (mode == 1) CU_TRY(cudaMemcpy(probs_out, dout.p, (size_t)n * A * sizeof(double), cudaMemcpyDeviceToHost));
+    else CU_TRY(cudaMemcpy(act_out, dout.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    Counters c;
+    CU_TRY(cudaMemcpy(&c, dc.p, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum; the reference panics in utils.rs:76");
+    return RSRL_OK;
+}
+
+int rsrl_policy_sample(int32_t policy, double epsilon, uint64_t seed, uint64_t draw, int64_t env_offset, int64_t n,
+                       int32_t n_actions, const double* q, int32_t* actions_out) {
+    if (!actions_out) return fail(RSRL_EINVAL, "null actions_out");
+    return policy_call(0, policy, epsilon, seed, draw, env_offset, n, n_actions, q, actions_out, nullptr);
+}
+int rsrl_policy_probs(int32_t policy, double epsilon, int64_t n, int32_t n_actions, const double* q, double* probs_out) {
+    if (!probs_out) return fail(RSRL_EINVAL, "null probs_out");
+    return policy_call(1, policy, epsilon, 0, 0, 0, n, n_actions, q, nullptr, probs_out);
+}
+int rsrl_policy_mode(int64_t n, int32_t n_actions, const double* q, int32_t* actions_out) {
+    if (!actions_out) return fail(RSRL_EINVAL, "null actions_out");
+    return policy_call(2, RSRL_GREEDY, 0.0, 0, 0, 0, n, n_actions, q, actions_out, nullptr);
+}
+
+int rsrl_trace_update(int32_t rule, double gamma, double lambda, double alpha, int64_t n, double* z_inout, const double* grad) {
+    if (rule < 0 || rule > 2 || n <= 0 || !z_inout || !grad) return fail(RSRL_EINVAL, "bad argument");
+    int rc = need_device();
+    if (rc) return rc;
+    DevBuf dz, dg;
+    CU_TRY(dz.alloc(n * sizeof(double))); CU_TRY(dg.alloc(n * sizeof(double)));
+    CU_TRY(cudaMemcpy(dz.p, z_inout, n * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dg.p, grad, n * sizeof(double), cudaMemcpyHostToDevice));
+    const double rate = rule == RSRL_TRACE_DUTCH ? gamma * lambda * (1.0 - alpha) : gamma * lambda;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    trace_update_kernel<double><<<blocks, threads>>>(rule, rate, n, dz.as<double>(), dg.as<double>());
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(z_inout, dz.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return RSRL_OK;
+}
+
+int rsrl_philox(uint64_t seed, uint64_t draw, uint32_t stream, int64_t env_offset, int64_t n, uint32_t* out) {
+    if (n <= 0 || !out) return fail(RSRL_EINVAL, "bad argument");
+    int rc = need_device();
+    if (rc) return rc;
+    DevBuf d;
+    CU_TRY(d.alloc((size_t)n * 16));
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    philox_kernel<<<blocks, threads>>>(seed, draw, stream, env_offset, n, d.as<uint32_t>());
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, d.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    return RSRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+// device.cuh — per-env device arithmetic of the rsrl hot path (sm_100a).
+//
+// Everything here is written from the reference's behaviour (file:line cited per
+// function, paths relative to the reference checkout), not from its code shape:
+// the reference allocates a Vec per observation / feature vector and re-projects
+// the state four times per step; here one env lives in the registers of one
+// thread, the Fourier features are generated from per-dimension sin/cos tables
+// (Kronecker structure) and never touch memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rsrl_b200.h"
+
+namespace rsrl {
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+// f64 physics: explicit round-to-nearest ops so that nvcc does not contract a*b+c into
+// DFMA — the reference (Rust, no FMA contraction) rounds after every operation.
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// clip!(lb, x, ub) = lb.max(ub.min(x))  (rsrl_domains/src/macros.rs:20-24); fmin/fmax drop NaN like Rust
+__device__ __forceinline__ double dclip(double lb, double x, double ub) { return fmax(lb, fmin(ub, x)); }
+// wrap!(lb, x, ub)  (macros.rs:3-18)
+__device__ __forceinline__ double dwrap(double lb, double x, double ub) {
+    double nx = x;
+    const double diff = dsub(ub, lb);
+    while (nx > ub) nx = dsub(nx, diff);
+    while (nx < lb) nx = dadd(nx, diff);
+    return nx;
+}
+
+#define RSRL_PI 3.14159265358979323846264338327950288
+
+template <typename R> struct RealOps;
+template <> struct RealOps<float> {
+    __device__ __forceinline__ static void sincospi(float x, float* s, float* c) { sincospif(x, s, c); }
+    __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    __device__ __forceinline__ static float abs(float a) { return fabsf(a); }
+    __device__ __forceinline__ static float lowest() { return -3.402823466e+38f; }  // magnitude only matters vs 1e-7
+    __device__ __forceinline__ static float clamp1(float x) { return fmaxf(-1.0f, fminf(1.0f, x)); }
+};
+template <> struct RealOps<double> {
+    __device__ __forceinline__ static void sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
+    __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    __device__ __forceinline__ static double abs(double a) { return fabs(a); }
+    __device__ __forceinline__ static double lowest() { return -1.7976931348623157e+308; }  // f64::MIN
+    __device__ __forceinline__ static double clamp1(double x) { return fmax(-1.0, fmin(1.0, x)); }
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. SC'11).  Project-defined stream layout
+// (SURVEY 7.2): key = seed, counter = (global env id, draw lo, draw hi, stream).
+// ---------------------------------------------------------------------------
+enum : uint32_t { STREAM_INIT = 0, STREAM_BEHAVIOUR = 1, STREAM_TARGET = 2 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 draw4(uint64_t seed, uint64_t env, uint64_t draw, uint32_t stream) {
+    return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)draw, (uint32_t)(draw >> 32), stream),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t word(const uint4& r, int d) { return d == 0 ? r.x : d == 1 ? r.y : d == 2 ? r.z : r.w; }
+
+// ---------------------------------------------------------------------------
+// Domains: one env step in registers.  `Domain::step` of rsrl_domains/src/lib.rs:434.
+// ---------------------------------------------------------------------------
+template <int DOM> struct Domain;
+
+// rsrl_domains/src/mountain_car/discrete.rs:8-22,56-102
+template <> struct Domain<RSRL_MOUNTAIN_CAR> {
+    static constexpr int D = 2, A = 3;
+    __host__ __device__ static constexpr double lo(int d) { return d == 0 ? -1.2 : -0.07; }
+    __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 0.6 : 0.07; }
+    __host__ __device__ static constexpr double start(int d) { return d == 0 ? -0.5 : 0.0; }
+    __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
+    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+        const double a = (double)(action - 1);                                        // ALL_ACTIONS = [-1, 0, 1]
+        const double dv = dadd(dmul(0.001, a), dmul(-0.0025, cos(dmul(3.0, s[0]))));  // :58
+        s[1] = dclip(-0.07, dadd(s[1], dv), 0.07);                                    // :63
+        s[0] = dclip(-1.2, dadd(s[0], s[1]), 0.6);                                    // :64 (uses the new v)
+        terminal = s[0] >= 0.6;                                                       // :77
+        reward = terminal ? 0.0 : -1.0;                                               // :88-92
+    }
+};
+
+// rsrl_domains/src/ode.rs:1-43 — k_i = f(...) * dx; y += (k1 + 2 k2 + 2 k3 + k4) / 6 in that association
+template <class Grad>
+__device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
+    double k1[4], k2[4], k3[4], k4[4], tmp[4];
+    f(y, k1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k1[i] = dmul(k1[i], dx); tmp[i] = dadd(y[i], ddiv(k1[i], 2.0)); }
+    f(tmp, k2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k2[i] = dmul(k2[i], dx); tmp[i] = dadd(y[i], ddiv(k2[i], 2.0)); }
+    f(tmp, k3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { k3[i] = dmul(k3[i], dx); tmp[i] = dadd(y[i], k3[i]); }
+    f(tmp, k4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k4[i] = dmul(k4[i], dx);
+        const double sum = dadd(dadd(dadd(k1[i], dmul(2.0, k2[i])), dmul(2.0, k3[i])), k4[i]);
+        y[i] = dadd(y[i], ddiv(sum, 6.0));
+    }
+}
+
+// rsrl_domains/src/cart_pole.rs:7-26,34-121
+template <> struct Domain<RSRL_CART_POLE> {
+    static constexpr int D = 4, A = 2;
+    static constexpr double TWELVE_DEGREES = RSRL_PI / 15.0;  // consts.rs:10
+    __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 2.4 : d == 1 ? 6.0 : d == 2 ? TWELVE_DEGREES : 2.0; }
+    __host__ __device__ static constexpr double lo(int d) { return -hi(d); }
+    __host__ __device__ static constexpr double start(int) { return 0.0; }
+    __device__ __forceinline__ static bool is_terminal(const double* s) {  // :83-97
+        return s[0] <= -2.4 || s[0] >= 2.4 || s[2] <= -TWELVE_DEGREES || s[2] >= TWELVE_DEGREES;
+    }
+    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+        const double force = action == 0 ? -10.0 : 10.0;  // ALL_ACTIONS :26
+        constexpr double POLE_MOMENT = 0.5 * 0.1, TOTAL_MASS = 1.0 + 0.1, FOUR_THIRDS = 4.0 / 3.0, G = 9.8;
+        auto grad = [force](const double* b, double* out) {  // :52-72
+            const double dx = b[1], theta = b[2], dtheta = b[3];
+            double sin_t, cos_t;
+            sincos(theta, &sin_t, &cos_t);
+            const double z = ddiv(dadd(force, dmul(dmul(dmul(POLE_MOMENT, dtheta), dtheta), sin_t)), TOTAL_MASS);
+            const double numer = dsub(dmul(G, sin_t), dmul(cos_t, z));
+            const double denom = dsub(dmul(FOUR_THIRDS, 0.5), dmul(dmul(POLE_MOMENT, cos_t), cos_t));
+            out[0] = dx;
+            out[2] = dtheta;
+            out[3] = ddiv(numer, denom);
+            out[1] = dsub(z, dmul(dmul(0.5, out[3]), cos_t));
+        };
+        double ns[4] = {s[0], s[1], s[2], s[3]};
+        runge_kutta4(grad, ns, 0.02);
+        s[0] = dclip(-2.4, ns[0], 2.4);  // :44-49
+        s[1] = dclip(-6.0, ns[1], 6.0);
+        s[2] = dclip(-TWELVE_DEGREES, ns[2], TWELVE_DEGREES);
+        s[3] = dclip(-2.0, ns[3], 2.0);
+        terminal = is_terminal(s);
+        reward = terminal ? -1.0 : 0.0;  // :23-24,103-107
+    }
+};
+
+// rsrl_domains/src/acrobot.rs:8-36,51-152 — quirks kept verbatim
+template <> struct Domain<RSRL_ACROBOT> {
+    static constexpr int D = 4, A = 3;
+    __host__ __device__ static constexpr double hi(int d) { return d < 2 ? RSRL_PI : d == 2 ? 4.0 * RSRL_PI : 9.0 * RSRL_PI; }
+    __host__ __device__ static constexpr double lo(int d) { return -hi(d); }
+    __host__ __device__ static constexpr double start(int) { return 0.0; }
+    __device__ __forceinline__ static bool is_terminal(const double* s) {  // :56-58
+        return dadd(cos(s[0]), cos(dadd(s[0], s[1]))) < -1.0;
+    }
+    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+        const double torque = (double)(action - 1);  // ALL_ACTIONS = [-1, 0, 1] :36
+        constexpr double G = 9.8, PI_OVER_2 = RSRL_PI / 2.0;
+        auto grad = [torque](const double* b, double* out) {  // :81-108 (M1=M2=L1=1, LC1=LC2=0.5, I1=I2=1)
+            const double theta1 = b[0], theta2 = b[1], dtheta1 = b[2], dtheta2 = b[3];
+            double sin_t2, cos_t2;
+            sincos(theta2, &sin_t2, &cos_t2);
+            // d1 = M1*LC1*LC1 + M2*(L1*L1 + LC2*LC2 + 2*L1*LC2*cos_t2) + I1 + I2
+            const double d1 = dadd(dadd(dadd(0.25, dmul(1.0, dadd(dadd(1.0, 0.25), dmul(1.0, cos_t2)))), 1.0), 1.0);
+            // d2 = M2*(LC2*LC2 + L1*LC2*cos_t2) + I2
+            const double d2 = dadd(dmul(1.0, dadd(0.25, dmul(0.5, cos_t2))), 1.0);
+            // phi2 = M2*LC2*G*cos(theta1 + theta2 - PI/2)
+            const double phi2 = dmul(dmul(0.5, G), cos(dsub(dadd(theta1, theta2), PI_OVER_2)));
+            // phi1 = -1*L1*LC2*dth2*dth2*sin_t2 - 2*M2*L1*LC2*dth2*dth1*sin_t2 + (M1*LC1 + M2*L1)*G*cos(th1 - PI/2) + phi2
+            const double t1 = dmul(dmul(dmul(-0.5, dtheta2), dtheta2), sin_t2);
+            const double t2 = dmul(dmul(dmul(1.0, dtheta2), dtheta1), sin_t2);  // 2.0*1*1*0.5 = 1.0 exactly
+            const double t3 = dmul(dmul(1.5, G), cos(dsub(theta1, PI_OVER_2)));
+            const double phi1 = dadd(dadd(dsub(t1, t2), t3), phi2);
+            out[0] = dtheta1;
+            out[1] = dtheta2;
+            // (torque + d2/d1*phi1 - M2*L1*LC2*dth1*dth1*sin_t2 - phi2) / (M2*LC2*LC2 + I2 - d2*d2/d1)
+            const double num = dsub(dsub(dadd(torque, dmul(ddiv(d2, d1), phi1)), dmul(dmul(dmul(0.5, dtheta1), dtheta1), sin_t2)), phi2);
+            const double den = dsub(dadd(0.25, 1.0), ddiv(dmul(d2, d2), d1));
+            out[2] = ddiv(num, den);
+            out[3] = ddiv(-dadd(dmul(d2, out[2]), phi1), d1);
+        };
+        double ns[4] = {s[0], s[1], s[2], s[3]};
+        runge_kutta4(grad, ns, 0.2);
+        s[0] = dwrap(-RSRL_PI, ns[0], RSRL_PI);  // :64-78
+        s[1] = dwrap(-RSRL_PI, ns[1], RSRL_PI);
+        s[2] = dclip(-4.0 * RSRL_PI, ns[2], 4.0 * RSRL_PI);
+        s[3] = dclip(-9.0 * RSRL_PI, ns[3], 9.0 * RSRL_PI);
+        terminal = is_terminal(s);
+        reward = terminal ? 0.0 : -1.0;  // :32-33,134-138
+    }
+};
+
+// start state of the episode beginning at batched step t (Domain::default() or U[lo,hi) from Philox)
+template <class Dom>
+__device__ __forceinline__ void fresh_state(double* s, int init_mode, const double* init_lo, const double* init_hi,
+                                            uint64_t seed, uint64_t g, uint64_t t) {
+    if (init_mode == RSRL_INIT_DEFAULT) {
+#pragma unroll
+        for (int d = 0; d < Dom::D; ++d) s[d] = Dom::start(d);
+    } else {
+        const uint4 r = draw4(seed, g, t, STREAM_INIT);
+#pragma unroll
+        for (int d = 0; d < Dom::D; ++d)
+            s[d] = dadd(init_lo[d], dmul(dsub(init_hi[d], init_lo[d]), dmul((double)word(r, d), 1.0 / 4294967296.0)));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Tensor-grid bases.  lfa::basis::Fourier::project computes, for every coefficient vector c in
+// {0..P}^D \ {0} (descending lexicographic order) phi = cos(pi * sum_d c_d * x^_d), then
+// .with_bias() appends 1.0.  Row k of that order has digits c = P - digit_d(k), and the skipped
+// all-zero vector would land exactly on the bias slot k = F-1 (cos 0 = 1), so the whole feature
+// vector is the real part of the tensor product  prod_d exp(i*pi*c_d*x^_d)  over the full grid.
+// We build per-dimension tables cos/sin(pi*c*x^_d), c = 1..P, by angle addition and combine.
+// Polynomial: phi = prod_d x_d^{c_d} on the raw state, same grid order (project-defined).
+// ---------------------------------------------------------------------------
+template <typename R, int D, int P, int BASIS>
+struct GridTables {
+    R c[D][P];  // c[d][j] = cos(pi*(j+1)*x^_d)   (Polynomial: x_d^(j+1))
+    R s[D][P];  // s[d][j] = sin(pi*(j+1)*x^_d)   (Polynomial: unused)
+};
+
+template <typename R, class Dom, int P, int BASIS>
+__device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom::D, P, BASIS>& t) {
+    using O = RealOps<R>;
+#pragma unroll
+    for (int d = 0; d < Dom::D; ++d) {
+        if (BASIS == RSRL_FOURIER) {
+            // scaled = (v - lo) / (hi - lo) in f64 exactly like the reference, then to the compute type
+            const R xh = (R)ddiv(dsub(st[d], Dom::lo(d)), dsub(Dom::hi(d), Dom::lo(d)));
+            R s1, c1;
+            O::sincospi(xh, &s1, &c1);
+            t.c[d][0] = c1;
+            t.s[d][0] = s1;
+#pragma unroll
+            for (int j = 1; j < P; ++j) {  // angle addition: (j+1)*theta = j*theta + theta
+                t.c[d][j] = O::fma(t.c[d][j - 1], c1, -(t.s[d][j - 1] * s1));
+                t.s[d][j] = O::fma(t.s[d][j - 1], c1, t.c[d][j - 1] * s1);
+            }
+        } else {
+            const R x = (R)st[d];
+            t.c[d][0] = x;
+#pragma unroll
+            for (int j = 1; j < P; ++j) t.c[d][j] = t.c[d][j - 1] * x;
+        }
+    }
+}
+
+// complex helper on (re, im) pairs with compile-time "c == 0 => 1 + 0i" shortcut
+template <typename R, int D, int P, int BASIS>
+struct GridBasis {
+    static constexpr int N1 = P + 1;
+    static constexpr int F = (D == 2) ? N1 * N1 : N1 * N1 * N1 * N1;
+    using Tab = GridTables<R, D, P, BASIS>;
+
+    // calls f(k, phi_k) for k = 0..F-1 in feature order; fully unrolled => k is a compile-time constant
+    template <class Fn>
+    __device__ __forceinline__ static void for_each(const Tab& t, Fn f) {
+        using O = RealOps<R>;
+        if (D == 2) {
+#pragma unroll
+            for (int i0 = 0; i0 < N1; ++i0) {
+#pragma unroll
+                for (int i1 = 0; i1 < N1; ++i1) {
+                    const int c0 = P - i0, c1 = P - i1;
+                    R phi;
+                    if (BASIS == RSRL_FOURIER) {
+                        if (c0 == 0 && c1 == 0) phi = (R)1;
+                        else if (c0 == 0) phi = t.c[1][c1 - 1];
+                        else if (c1 == 0) phi = t.c[0][c0 - 1];
+                        else phi = O::fma(t.c[0][c0 - 1], t.c[1][c1 - 1], -(t.s[0][c0 - 1] * t.s[1][c1 - 1]));
+                    } else {
+                        if (c0 == 0 && c1 == 0) phi = (R)1;
+                        else if (c0 == 0) phi = t.c[1][c1 - 1];
+                        else if (c1 == 0) phi = t.c[0][c0 - 1];
+                        else phi = t.c[0][c0 - 1] * t.c[1][c1 - 1];
+                    }
+                    f(i0 * N1 + i1, phi);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i0 = 0; i0 < N1; ++i0) {
+#pragma unroll
+                for (int i1 = 0; i1 < N1; ++i1) {
+                    const int c0 = P - i0, c1 = P - i1;
+                    // z01 = e(c0) * e(c1)
+                    R re01, im01;
+                    cmul(t, 0, c0, 1, c1, re01, im01);
+#pragma unroll
+                    for (int i2 = 0; i2 < N1; ++i2) {
+                        const int c2 = P - i2;
+                        R re012, im012;
+                        cmul_acc(t, re01, im01, 2, c2, re012, im012);
+#pragma unroll
+                        for (int i3 = 0; i3 < N1; ++i3) {
+                            const int c3 = P - i3;
+                            R phi;
+                            if (BASIS == RSRL_FOURIER) {
+                                if (c3 == 0) phi = re012;
+                                else phi = O::fma(re012, t.c[3][c3 - 1], -(im012 * t.s[3][c3 - 1]));
+                            } else {
+                                phi = c3 == 0 ? re012 : re012 * t.c[3][c3 - 1];
+                            }
+                            f(((i0 * N1 + i1) * N1 + i2) * N1 + i3, phi);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ static void cmul(const Tab& t, int d0, int c0, int d1, int c1, R& re, R& im) {
+        using O = RealOps<R>;
+        const R a = c0 == 0 ? (R)1 : t.c[d0][c0 - 1], b = (c0 == 0 || BASIS != RSRL_FOURIER) ? (R)0 : t.s[d0][c0 - 1];
+        if (c1 == 0) { re = a; im = b; return; }
+        if (BASIS == RSRL_FOURIER) {
+            re = O::fma(a, t.c[d1][c1 - 1], -(b * t.s[d1][c1 - 1]));
+            im = O::fma(a, t.s[d1][c1 - 1], b * t.c[d1][c1 - 1]);
+        } else { re = a * t.c[d1][c1 - 1]; im = (R)0; }
+    }
+    __device__ __forceinline__ static void cmul_acc(const Tab& t, R a, R b, int d1, int c1, R& re, R& im) {
+        using O = RealOps<R>;
+        if (c1 == 0) { re = a; im = b; return; }
+        if (BASIS == RSRL_FOURIER) {
+            re = O::fma(a, t.c[d1][c1 - 1], -(b * t.s[d1][c1 - 1]));
+            im = O::fma(a, t.s[d1][c1 - 1], b * t.c[d1][c1 - 1]);
+        } else { re = a * t.c[d1][c1 - 1]; im = (R)0; }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// argmax family + policies
+// ---------------------------------------------------------------------------
+// utils.rs:6-21 argmaxima: returns the tie set as a bit mask; a value within 1e-7 of `max` joins
+// without raising `max`.
+template <typename R, int A>
+__device__ __forceinline__ uint32_t argmaxima(const R* q, int& count) {
+    using O = RealOps<R>;
+    R mx = O::lowest();
+    uint32_t mask = 0;
+    count = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+        if (O::abs(q[i] - mx) < (R)1e-7) { mask |= 1u << i; ++count; }
+        else if (q[i] > mx) { mx = q[i]; mask = 1u << i; count = 1; }
+    }
+    return mask;
+}
+
+// core.rs:96-105 find_max: exact compare, the LAST maximal index wins, NaN replaces the accumulator
+template <typename R, int A>
+__device__ __forceinline__ int find_max(const R* q, R& mx) {
+    int idx = 0;
+    mx = q[0];
+#pragma unroll
+    for (int i = 1; i < A; ++i) if (!(mx > q[i])) { idx = i; mx = q[i]; }
+    return idx;
+}
+
+// utils.rs:23-34 argmax_first: new best only if y - x > 1e-7, first wins
+template <typename R, int A>
+__device__ __forceinline__ int argmax_first(const R* q) {
+    using O = RealOps<R>;
+    int idx = 0;
+    R x = O::lowest();
+#pragma unroll
+    for (int j = 0; j < A; ++j) if (q[j] - x > (R)1e-7) { idx = j; x = q[j]; }
+    return idx;
+}
+
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) {
+    for (int i = 0; i < n; ++i) mask &= mask - 1;
+    return __ffs(mask) - 1;
+}
+
+struct PolicyParams {
+    int policy;           // rsrl_policy_t
+    uint32_t eps_thresh;  // floor(eps * 2^32)
+    int eps_always;       // eps >= 1 (rand's gen_bool(1.0) is true without drawing)
+    uint64_t seed;
+};
+
+// Policy::sample — greedy.rs:77-81 (argmax_choose_rng: RNG only on ties), epsilon_greedy.rs:74-80,
+// random.rs:43-45.  rnd.x -> gen_bool(eps), rnd.y -> Uniform(0, A), rnd.z -> choose among maxima.
+template <typename R, int A>
+__device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, uint64_t g, uint64_t draw,
+                                             uint32_t stream, bool& nonfinite) {
+    if (p.policy != RSRL_GREEDY) {
+        const uint4 r = draw4(p.seed, g, draw, stream);
+        const bool explore = p.policy == RSRL_RANDOM || p.eps_always || r.x < p.eps_thresh;
+        if (explore) return (int)__umulhi(r.y, (uint32_t)A);
+        int cnt;
+        const uint32_t mask = argmaxima<R, A>(q, cnt);
+        if (cnt == 0) { nonfinite = true; return 0; }
+        if (cnt == 1) return __ffs(mask) - 1;
+        return nth_set_bit(mask, (int)__umulhi(r.z, (uint32_t)cnt));
+    }
+    int cnt;
+    const uint32_t mask = argmaxima<R, A>(q, cnt);
+    if (cnt == 0) { nonfinite = true; return 0; }
+    if (cnt == 1) return __ffs(mask) - 1;
+    const uint4 r = draw4(p.seed, g, draw, stream);  // rare: only on ties
+    return nth_set_bit(mask, (int)__umulhi(r.z, (uint32_t)cnt));
+}
+
+// Function<(S,)>::evaluate of the policy (greedy.rs:30-44, epsilon_greedy.rs:38-45)
+template <typename R, int A>
+__device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p) {
+    if (policy == RSRL_RANDOM) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) p[i] = (R)1 / (R)A;
+        return;
+    }
+    int cnt;
+    const uint32_t mask = argmaxima<R, A>(q, cnt);
+    const R pg = (R)1 / (R)cnt;
+#pragma unroll
+    for (int i = 0; i < A; ++i) p[i] = ((mask >> i) & 1u) ? pg : (R)0;
+    if (policy == RSRL_EPSILON_GREEDY) {
+        const R pr = eps / (R)A;
+#pragma unroll
+        for (int i = 0; i < A; ++i) p[i] = pr + p[i] * ((R)1 - eps);
+    }
+}
+
+// traces.rs:196-240
+template <typename R>
+__device__ __forceinline__ R trace_rule(int rule, R rate, R z, R grad) {
+    const R v = RealOps<R>::fma(rate, z, grad);
+    return rule == RSRL_TRACE_REPLACE ? RealOps<R>::clamp1(v) : v;
+}
+
+}  // namespace rsrl

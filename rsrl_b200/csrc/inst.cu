@@ -1,0 +1,79 @@
+// inst.cu — explicit kernel instantiations for one (dtype, domain) pair.
+// Compiled six times: -DRSRL_REAL=float|double -DRSRL_DOM=0|1|2 -DRSRL_SUFFIX=f32_d0 ...
+#include "launch.h"
+
+namespace rsrl {
+
+typedef RSRL_REAL R;
+constexpr int DOM = RSRL_DOM;
+
+template <int BASIS, int P, int AW, int MODE, bool EXT>
+static cudaError_t launch_one(const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = fused_step_kernel<R, DOM, BASIS, P, AW, MODE, EXT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, block, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int BASIS, int P, int AW>
+static cudaError_t launch_mode(int mode, bool ext, const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    if (mode == RSRL_SHARED) return ext ? launch_one<BASIS, P, AW, RSRL_SHARED, true>(a, grid, block, smem, st)
+                                        : launch_one<BASIS, P, AW, RSRL_SHARED, false>(a, grid, block, smem, st);
+    return ext ? launch_one<BASIS, P, AW, RSRL_PER_ENV, true>(a, grid, block, smem, st)
+               : launch_one<BASIS, P, AW, RSRL_PER_ENV, false>(a, grid, block, smem, st);
+}
+
+template <int BASIS, int P, int AW>
+static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
+    const int block = 128;
+    const int grid = (int)((e.n + block - 1) / block);
+    basis_eval_kernel<R, DOM, BASIS, P, AW><<<grid, block, 0, st>>>(e.mode, e.n, e.states, static_cast<const R*>(e.W),
+                                                                     e.w_env_stride, e.out, e.act_out, e.pol, e.draw,
+                                                                     e.env_offset, e.counters);
+    return cudaGetLastError();
+}
+
+// (basis, order) pairs built for this domain.  MountainCar (D = 2) unrolls any order up to 7;
+// the D = 4 domains are fully unrolled only up to order 3 here (Fourier(7) on Acrobot = 4096
+// features takes the tiled path).
+#if RSRL_DOM == 0
+#define RSRL_COMBOS(X) X(RSRL_FOURIER, 1) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_FOURIER, 5) X(RSRL_FOURIER, 7) \
+                       X(RSRL_POLYNOMIAL, 2) X(RSRL_POLYNOMIAL, 3)
+#else
+#define RSRL_COMBOS(X) X(RSRL_FOURIER, 1) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_POLYNOMIAL, 2)
+#endif
+
+#define RSRL_CAT_(a, b) a##b
+#define RSRL_CAT(a, b) RSRL_CAT_(a, b)
+
+cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid,
+                                                 int block, size_t smem, cudaStream_t st) {
+    constexpr int A = Domain<DOM>::A;
+#define X(B, P)                                                                                  \
+    if (k.basis == B && k.order == P) {                                                          \
+        if (k.aw == A) return launch_mode<B, P, A>(mode, ext, a, grid, block, smem, st);         \
+        if (k.aw == 1) return launch_mode<B, P, 1>(mode, ext, a, grid, block, smem, st);         \
+    }
+    RSRL_COMBOS(X)
+#undef X
+    return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t RSRL_CAT(launch_eval_, RSRL_SUFFIX)(const BasisKey& k, const EvalArgs& e, cudaStream_t st) {
+    constexpr int A = Domain<DOM>::A;
+#define X(B, P)                                                   \
+    if (k.basis == B && k.order == P) {                           \
+        if (k.aw == A) return eval_one<B, P, A>(e, st);           \
+        if (k.aw == 1) return eval_one<B, P, 1>(e, st);           \
+    }
+    RSRL_COMBOS(X)
+#undef X
+    return cudaErrorInvalidDeviceFunction;
+}
+
+}  // namespace rsrl

@@ -1,0 +1,41 @@
+// launch.h — type-erased host launchers for the templated kernels (one instantiation TU per dtype/domain).
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace rsrl {
+
+struct BasisKey {
+    int dtype;   // rsrl_dtype_t
+    int domain;  // rsrl_domain_t
+    int basis;   // rsrl_basis_t
+    int order;   // P
+    int aw;      // weight columns: n_actions, or 1 for TD prediction
+};
+
+struct EvalArgs {
+    int mode;  // 0 features, 1 Q, 2 sample, 3 find_max
+    int64_t n;
+    const double* states;
+    const void* W;
+    int64_t w_env_stride;
+    double* out;
+    int32_t* act_out;
+    PolicyParams pol;
+    uint64_t draw;
+    int64_t env_offset;
+    Counters* counters;
+};
+
+// returns cudaErrorInvalidDeviceFunction when the combination was not instantiated
+typedef cudaError_t (*fused_launch_fn)(const BasisKey&, int weight_mode, bool ext, const StepArgs&, int grid, int block,
+                                       size_t smem, cudaStream_t);
+typedef cudaError_t (*eval_launch_fn)(const BasisKey&, const EvalArgs&, cudaStream_t);
+
+#define RSRL_DECL_INST(SUFFIX)                                                                                      \
+    cudaError_t launch_fused_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t); \
+    cudaError_t launch_eval_##SUFFIX(const BasisKey&, const EvalArgs&, cudaStream_t);
+RSRL_DECL_INST(f32_d0) RSRL_DECL_INST(f32_d1) RSRL_DECL_INST(f32_d2)
+RSRL_DECL_INST(f64_d0) RSRL_DECL_INST(f64_d1) RSRL_DECL_INST(f64_d2)
+
+}  // namespace rsrl

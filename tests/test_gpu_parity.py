@@ -1,0 +1,460 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): action indices / episode step counts bit-exact; f64 physics within a few ulp of the
+libm-based oracle; Q weights within a stated tolerance — 1e-9 for dtype f64, the fp32 tolerances written
+next to each f32 assertion.  Reference golden vectors (cart_pole.rs:144-183, greedy.rs:96-168, ...) are
+re-checked on the device as well.
+"""
+import numpy as np
+import pytest
+
+from rsrl_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+MC, CP, AC = abi.MOUNTAIN_CAR, abi.CART_POLE, abi.ACROBOT
+
+
+@pytest.fixture(scope="module")
+def E(rsrl):
+    from rsrl_b200 import engine
+    assert abi.load().rsrl_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return engine
+
+
+# ---------------------------------------------------------------------------------------------
+# RNG: integer work, bit-exact
+# ---------------------------------------------------------------------------------------------
+def test_philox_bit_exact(E, oracle):
+    got = E.philox(seed=0x1234567890ABCDEF, draw=(1 << 33) + 5, stream=2, env_offset=7, n=1000)
+    want = np.array([oracle.draw(0x1234567890ABCDEF, 7 + i, (1 << 33) + 5, 2) for i in range(1000)])
+    assert (got == want).all()
+    kat = E.philox(seed=0, draw=0, stream=0, env_offset=0, n=1)[0]
+    assert [int(x) for x in kat] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 domains
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("action,sign", [(0, -1.0), (1, 1.0)])
+def test_cartpole_golden_on_device(E, action, sign):
+    g1 = np.array([0.0032931628891235, 0.3293940797883472, -0.0029499634056967, -0.2951522145037250]) * sign
+    g2 = np.array([0.0131819582085161, 0.6597158115002169, -0.0118185373734479, -0.5921703414056713]) * sign
+    s1, r1, t1 = E.domain_step(CP, np.zeros((1, 4)), [action])
+    s2, r2, t2 = E.domain_step(CP, s1, [action])
+    assert np.abs(s1[0] - g1).max() < 1e-7 and np.abs(s2[0] - g2).max() < 1e-7  # reference tolerance
+    assert np.abs(s1[0] - g1).max() < 1e-15 and np.abs(s2[0] - g2).max() < 1e-15
+    assert r1[0] == 0.0 and not t1[0]
+
+
+def test_mountain_car_terminal_predicate_on_device(E):
+    X = 0.6
+    s = np.array([[-0.5, 0.0], [X, -0.05], [X, 0.0], [X, 0.05], [X - 1e-4 * X, 0.0], [X + 1e-4 * X, 0.0]])
+    assert E.domain_is_terminal(MC, s).tolist() == [0, 1, 1, 1, 0, 1]
+    assert not E.domain_is_terminal(CP, np.zeros((1, 4)))[0] and not E.domain_is_terminal(AC, np.zeros((1, 4)))[0]
+
+
+@pytest.mark.parametrize("domain", [MC, CP, AC])
+def test_domain_step_matches_oracle(E, oracle, domain):
+    D, A = oracle.domain_dims(domain)
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(domain)
+    n = 4096
+    s = rng.uniform(lo, hi, size=(n, D))
+    s[:64] = np.where(rng.random((64, D)) < 0.5, lo, hi)  # corners: clip / terminal edges
+    a = rng.integers(0, A, n).astype(np.int32)
+    got_s, got_r, got_t = E.domain_step(domain, s, a)
+    want_s, want_r, want_t = oracle.domain_step(domain, s, a)
+    # f64 physics; the only difference is CUDA's sin/cos vs glibc's (both < 1 ulp)
+    scale = np.maximum(np.abs(want_s), 1.0)
+    assert (np.abs(got_s - want_s) / scale).max() < 1e-13
+    assert (got_r == want_r).all() and (got_t == want_t).all()
+    assert (got_s == want_s).mean() > 0.9  # mostly bit-identical
+
+
+def test_domain_step_multi_step_trajectory(E, oracle):
+    # 500 steps of MountainCar bang-bang control: positions must track the oracle to 1e-12
+    n = 256
+    rng = np.random.default_rng(5)
+    s_g = np.tile([-0.5, 0.0], (n, 1)) + rng.uniform(-0.1, 0.1, (n, 2)) * [1, 0]
+    s_o = s_g.copy()
+    for t in range(500):
+        a = (s_o[:, 1] >= 0).astype(np.int32) * 2
+        s_g, _, tg = E.domain_step(MC, s_g, a)
+        s_o, _, to = oracle.domain_step(MC, s_o, a)
+        assert (tg == to).all()
+    assert np.abs(s_g - s_o).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# K2/K3 basis projection + LFA evaluate
+# ---------------------------------------------------------------------------------------------
+COMBOS = [(MC, abi.FOURIER, 5), (MC, abi.FOURIER, 3), (MC, abi.FOURIER, 7), (MC, abi.POLYNOMIAL, 3),
+          (CP, abi.FOURIER, 3), (AC, abi.FOURIER, 2), (CP, abi.POLYNOMIAL, 2)]
+
+
+@pytest.mark.parametrize("domain,basis,order", COMBOS)
+@pytest.mark.parametrize("dtype,tol", [(abi.F64, 2e-14), (abi.F32, 4e-6)])
+def test_basis_project_matches_oracle(E, oracle, domain, basis, order, dtype, tol):
+    cfg = abi.default_config(domain=domain, basis=basis, basis_order=order, dtype=dtype)
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(order)
+    s = rng.uniform(lo, hi, size=(512, len(lo)))
+    s[0], s[1] = lo, hi
+    got, want = E.basis_project(cfg, s), oracle.project(cfg, s)
+    assert got.shape == want.shape
+    scale = np.maximum(np.abs(want), 1.0)
+    assert (np.abs(got - want) / scale).max() < tol * (order if basis == abi.FOURIER else 1)
+    assert (got[:, -1] == 1.0).all()
+
+
+@pytest.mark.parametrize("domain,basis,order", COMBOS[:5])
+@pytest.mark.parametrize("dtype,tol", [(abi.F64, 1e-12), (abi.F32, 2e-4)])
+def test_lfa_evaluate_matches_oracle(E, oracle, domain, basis, order, dtype, tol):
+    cfg = abi.default_config(domain=domain, basis=basis, basis_order=order, dtype=dtype)
+    D, A = oracle.domain_dims(domain)
+    F = oracle.n_features(cfg)
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(7)
+    s = rng.uniform(lo, hi, size=(300, D))
+    W = rng.normal(size=(F, A))
+    got, want = E.lfa_evaluate(cfg, W, s), oracle.evaluate(cfg, W, s)
+    assert np.abs(got - want).max() < tol * np.sqrt(F)
+
+
+@pytest.mark.parametrize("dtype,tol", [(abi.F64, 1e-13), (abi.F32, 1e-6)])
+def test_lfa_update_index_matches_oracle(E, oracle, dtype, tol):
+    cfg = abi.default_config(dtype=dtype, lr=0.05)
+    rng = np.random.default_rng(2)
+    W0 = rng.normal(size=(36, 3))
+    s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(50, 2))
+    a = rng.integers(0, 3, 50)
+    err = rng.normal(size=50)
+    got = E.lfa_update_index(cfg, W0, s, a, err)
+    want = W0.copy()
+    for i in range(50):  # SGD: W[:, a] += (lr * err) * phi(s)
+        want = oracle.update_index(cfg, want, s[i], a[i], 0.05 * err[i])
+    assert np.abs(got - want).max() < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 policies: the reference's MockQ tests run against the device kernels
+# ---------------------------------------------------------------------------------------------
+def test_greedy_reference_cases_on_device(E):
+    g = lambda q: int(E.policy_sample(abi.GREEDY, 0.0, 0, 0, 0, [q])[0])
+    assert g([1.0]) == 0 and g([-100.0]) == 0
+    assert g([10.0, 1.0]) == 0 and g([1.0, 10.0]) == 1
+    assert g([-10.0, -1.0]) == 1 and g([-1.0, -10.0]) == 0
+    assert g([10.0, -1.0]) == 0 and g([-10.0, 1.0]) == 1 and g([1.0, -10.0]) == 0 and g([-1.0, 10.0]) == 1
+    assert g([-123.1, 123.1, 250.5, -1240.0, -4500.0, 10000.0, 20.1]) == 5
+    assert g([1e-7, 2e-7]) == 1
+
+
+def test_policy_probabilities_on_device(E):
+    p = E.policy_probs(abi.GREEDY, 0.0, [[1e-7] * 4, [1e-7, 2e-7, 3e-7, 4e-7]])
+    assert np.abs(p - [[0.25] * 4, [0, 0, 0, 1]]).max() < 1e-6
+    p = E.policy_probs(abi.EPSILON_GREEDY, 0.5, [[1, 0, 0, 0, 0], [0, 0, 0, 0, 1], [1, 0, 0, 0, 1]])
+    assert np.abs(p - [[0.6, 0.1, 0.1, 0.1, 0.1], [0.1, 0.1, 0.1, 0.1, 0.6], [0.35, 0.1, 0.1, 0.1, 0.35]]).max() < 1e-6
+    p = E.policy_probs(abi.EPSILON_GREEDY, 1.0, [[-1.0, 0, 0, 0]])
+    assert np.abs(p - 0.25).max() < 1e-6
+
+
+def test_policy_sample_bit_exact_vs_oracle(E, oracle):
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=(5000, 3))
+    q[:1000] = np.round(q[:1000])          # many exact ties
+    q[1000:1500, 1] = q[1000:1500, 0] + 5e-8  # inside the 1e-7 tolerance
+    for policy, eps in [(abi.GREEDY, 0.0), (abi.EPSILON_GREEDY, 0.3), (abi.EPSILON_GREEDY, 1.0), (abi.RANDOM, 0.0)]:
+        got = E.policy_sample(policy, eps, 99, 12, 1000, q)
+        want = oracle.policy_sample_batch(policy, eps, 99, 12, 1000, q)
+        assert (got == want).all()
+    assert (E.policy_mode(q) == [oracle.find_max(r)[0] for r in q]).all()
+
+
+def test_epsilon_greedy_frequencies_on_device(E):
+    acts = E.policy_sample(abi.EPSILON_GREEDY, 0.5, 1, 0, 0, np.tile([1.0, 0.0], (10000, 1)))
+    assert abs(0.75 - (acts == 0).mean()) < 0.05  # epsilon_greedy.rs:96-113
+    acts = E.policy_sample(abi.RANDOM, 0.0, 1, 0, 0, np.zeros((10000, 2)))
+    assert abs(0.5 - (acts == 0).mean()) < 0.05   # random.rs:58-76
+
+
+def test_nonfinite_q_is_an_error(E):
+    with pytest.raises(abi.RsrlError) as ei:
+        E.policy_sample(abi.GREEDY, 0.0, 0, 0, 0, [[np.nan, np.nan]])
+    assert ei.value.code == abi.ENONFINITE  # the reference panics (utils.rs:76)
+
+
+# ---------------------------------------------------------------------------------------------
+# K6 traces
+# ---------------------------------------------------------------------------------------------
+def test_trace_rules_on_device(E, oracle):
+    z = E.trace_update(abi.TRACE_ACCUMULATE, 0.95, 0.7, 0.0, np.zeros(1), np.ones(1))
+    z = E.trace_update(abi.TRACE_ACCUMULATE, 0.95, 0.7, 0.0, z, np.zeros(1))
+    assert abs(z[0] - 0.665) < 1e-12  # traces.rs:121-125
+    rng = np.random.default_rng(0)
+    z0, g = rng.normal(size=1000), rng.normal(size=1000)
+    for rule in (abi.TRACE_ACCUMULATE, abi.TRACE_REPLACE, abi.TRACE_DUTCH):
+        got, want = E.trace_update(rule, 0.99, 0.7, 0.1, z0, g), oracle.trace_update(rule, 0.99, 0.7, 0.1, z0, g)
+        assert np.abs(got - want).max() < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------
+# fused engine, free running, dtype f64: bit-exact actions and step counts
+# ---------------------------------------------------------------------------------------------
+def _mc_cfg(**kw):
+    base = dict(n_envs=64, dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[-0.4, 0.0],
+                max_episode_steps=300, seed=11, record_td_error=1)
+    base.update(kw)
+    return abi.default_config(**base)
+
+
+def _compare_engines(e, o, w_tol, s_tol=1e-9):
+    assert (e.actions() == o.actions()).all()
+    assert (e.episode_steps() == o.episode_steps()).all()
+    for x, y in zip(e.env_stats(), o.env_stats()):
+        assert (x == y).all()
+    se, so = e.stats(), o.stats()
+    for k in ("total_steps", "total_episodes", "terminal_episodes", "batch_steps", "nonfinite"):
+        assert se[k] == so[k], k
+    rel = lambda a, b: np.abs(a - b).max() / max(1.0, np.abs(b).max())
+    assert rel(e.states(), o.states()) < s_tol
+    assert rel(e.weights(), o.weights()) < w_tol
+    assert rel(e.td_errors(), o.td_errors()) < max(w_tol * 100, 1e-9)
+
+
+ALGOS = [
+    ("qlearning_greedy", dict(algo=abi.QLEARNING, policy=abi.GREEDY)),
+    ("qlearning_eps", dict(algo=abi.QLEARNING, policy=abi.EPSILON_GREEDY, epsilon=0.1)),
+    ("sarsa_eps", dict(algo=abi.SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=0.01)),
+    ("expected_sarsa_eps", dict(algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, lr=0.01)),
+    ("sarsa_lambda_replace", dict(algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99,
+                                  trace_rule=abi.TRACE_REPLACE)),
+    ("q_lambda_accumulate", dict(algo=abi.Q_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.002, gamma=0.99,
+                                 trace_rule=abi.TRACE_ACCUMULATE)),
+    ("td_lambda", dict(algo=abi.TD_LAMBDA, policy=abi.RANDOM, gamma=0.99, trace_rule=abi.TRACE_ACCUMULATE,
+                       update_scale=abi.SCALE_MEAN, lambda_=0.5)),
+    ("td0", dict(algo=abi.TD0, policy=abi.RANDOM, gamma=0.99, lr=0.01)),
+]
+
+
+@pytest.mark.parametrize("name,kw", ALGOS, ids=[a[0] for a in ALGOS])
+@pytest.mark.parametrize("mode", [abi.SHARED, abi.PER_ENV], ids=["shared", "per_env"])
+def test_engine_free_run_f64_bit_exact_actions(E, oracle, name, kw, mode):
+    # TDLambda has no step size at all (td_lambda.rs:56-59: W += td_error * z), so with Fourier features it
+    # diverges geometrically exactly like the reference would; compare (relative tolerance) over a short run.
+    chunks = (1, 7, 12) if name == "td_lambda" else (1, 7, 392)
+    cfg = _mc_cfg(weight_mode=mode, **kw)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        for chunk in chunks:
+            e.step(chunk)
+            o.step(chunk)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9)
+        if cfg.algo in (abi.SARSA_LAMBDA, abi.Q_LAMBDA, abi.TD_LAMBDA):
+            assert np.abs(e.traces() - o.traces()).max() < 1e-9
+        assert name == "td_lambda" or o.stats()["total_episodes"] > 0
+
+
+def test_engine_q_learning_example_n1(E, oracle):
+    """BASELINE config 1: exactly examples/q_learning.rs (1 env, default start, SGD(0.001), gamma 0.9,
+    greedy) with a step cap; episode lengths must match the oracle bit for bit."""
+    cfg = abi.default_config(dtype=abi.F64, max_episode_steps=10000)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(30000)
+        o.step(30000)
+        e.sync()
+        _n, _l, h_e = e.env_stats()
+        _n2, _l2, h_o = o.env_stats()
+        assert (h_e == h_o).all() and (_n == _n2).all() and _n[0] >= 3
+        assert (e.actions() == o.actions()).all() and (e.episode_steps() == o.episode_steps()).all()
+        assert np.abs(e.weights() - o.weights()).max() < 1e-9
+
+
+def test_n1_shared_equals_per_env(E):
+    """With N = 1 and SUM scaling the batched semantics reduce to the reference loop: both weight modes agree."""
+    outs = []
+    for mode in (abi.SHARED, abi.PER_ENV):
+        cfg = abi.default_config(dtype=abi.F64, max_episode_steps=2000, weight_mode=mode)
+        with E.Engine(cfg) as e:
+            e.step(5000)
+            e.sync()
+            outs.append((e.weights().reshape(36, 3), e.states(), e.env_stats()[2]))
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all() and (outs[0][2] == outs[1][2]).all()
+
+
+@pytest.mark.parametrize("domain,order,algo", [(CP, 3, abi.SARSA), (AC, 2, abi.EXPECTED_SARSA)])
+def test_engine_free_run_d4_domains(E, oracle, domain, order, algo):
+    cfg = abi.default_config(domain=domain, basis_order=order, algo=algo, policy=abi.EPSILON_GREEDY, epsilon=0.1,
+                             n_envs=33, dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.05] * 4, init_hi=[0.05] * 4,
+                             max_episode_steps=100, seed=5, gamma=0.99, lr=0.01, alpha=1.0, record_td_error=1,
+                             update_scale=abi.SCALE_MEAN)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(150)
+        o.step(150)
+        e.sync()
+        _compare_engines(e, o, w_tol=1e-9, s_tol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------
+# dtype f32 (bench dtype): teacher-forced single steps within fp32 tolerance + short free run
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw", ALGOS[:4], ids=[a[0] for a in ALGOS[:4]])
+def test_engine_f32_teacher_forced(E, oracle, name, kw):
+    """Each step starts from the same inputs on both sides (oracle state/weights copied from the device):
+    next states within 1e-12 (f64 physics), TD errors within 2e-4, weights within 1e-5 (fp32 features/Q),
+    actions identical wherever the oracle's decision margin exceeds the fp32 resolution of Q."""
+    cfg = _mc_cfg(dtype=abi.F32, n_envs=512, **kw)
+    rng = np.random.default_rng(4)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        W = rng.normal(size=(36, 3)) * 0.5
+        e.set_weights(W)
+        for t in range(20):
+            o.set_states(e.states())
+            o.set_weights(e.weights())
+            q = oracle.evaluate(cfg, e.weights(), e.states())
+            srt = np.sort(q, axis=1)
+            margin = srt[:, -1] - srt[:, -2]
+            e.step(1)
+            o.step(1)
+            e.sync()
+            safe = margin > 1e-4
+            assert safe.mean() > 0.95
+            assert (e.actions()[safe] == o.actions()[safe]).all()
+            same = e.actions() == o.actions()
+            assert np.abs(e.states()[same] - o.states()[same]).max() < 1e-12
+            assert np.abs(e.td_errors()[same] - o.td_errors()[same]).max() < 2e-4
+            if same.all():
+                assert np.abs(e.weights() - o.weights()).max() < 1e-5
+
+
+def test_engine_f32_free_run_short_horizon(E, oracle):
+    cfg = _mc_cfg(dtype=abi.F32, n_envs=256, seed=21)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(100)
+        o.step(100)
+        e.sync()
+        assert o.min_gap() > 1e-5, "oracle run came too close to a tie for an fp32 comparison"
+        assert (e.actions() == o.actions()).all() and (e.episode_steps() == o.episode_steps()).all()
+        assert np.abs(e.weights() - o.weights()).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# trait-level entry points (Function::evaluate, Policy::sample/mode, Handler::handle)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo,policy", [(abi.QLEARNING, abi.GREEDY), (abi.SARSA, abi.EPSILON_GREEDY),
+                                         (abi.EXPECTED_SARSA, abi.EPSILON_GREEDY)])
+def test_handle_entry_point_matches_oracle(E, oracle, algo, policy):
+    cfg = _mc_cfg(algo=algo, policy=policy, epsilon=0.25, alpha=0.7, lr=0.02, n_envs=100)
+    rng = np.random.default_rng(9)
+    W = rng.normal(size=(36, 3))
+    s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(100, 2))
+    a = rng.integers(0, 3, 100).astype(np.int32)
+    ns, r, term = oracle.domain_step(MC, s, a)
+    term[:10] = 1
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.set_weights(W)
+        o.set_weights(W)
+        assert np.abs(e.evaluate(s) - oracle.evaluate(cfg, W, s)).max() < 1e-12
+        assert (e.mode(s) == [oracle.find_max(q)[0] for q in oracle.evaluate(cfg, W, s)]).all()
+        assert (e.sample(s, draw=3) == oracle.policy_sample_batch(policy, 0.25, cfg.seed, 3, 0, oracle.evaluate(cfg, W, s))).all()
+        td_e = e.handle(s, a, r, ns, term, draw_idx=17)
+        td_o = o.handle(s, a, r, ns, term, draw_idx=17)
+        assert np.abs(td_e - td_o).max() < 1e-12
+        assert np.abs(e.weights() - o.weights()).max() < 1e-12
+
+
+def test_drop_in_loop_equals_fused_engine(E, oracle):
+    """The reference's driver loop written against the trait-level entry points
+    (env.transition -> agent.handle -> policy.sample; examples/q_learning.rs:40-52) gives the same
+    weights as the fused engine."""
+    cfg = _mc_cfg(n_envs=16, max_episode_steps=0, seed=2)
+    with E.Engine(cfg) as fused, E.Engine(cfg) as unfused:
+        fused.step(50)
+        fused.sync()
+        s = unfused.states()
+        for t in range(50):
+            a = unfused.sample(s, draw=t)
+            ns, r, term = E.domain_step(MC, s, a)
+            unfused.handle(s, a, r, ns, term, draw_idx=t)
+            assert not term.any()
+            s = ns
+        assert np.abs(fused.states() - s).max() == 0.0
+        assert np.abs(fused.weights() - unfused.weights()).max() < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _cfg2(**kw):
+    base = dict(n_envs=65536, dtype=abi.F32, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[-0.4, 0.0],
+                max_episode_steps=1000, seed=0, update_scale=abi.SCALE_MEAN)
+    base.update(kw)
+    return abi.default_config(**base)
+
+
+def test_cfg2_full_size_properties(E, oracle):
+    cfg = _cfg2()
+    runs = []
+    for _ in range(2):
+        with E.Engine(cfg) as e:
+            e.step(300)
+            e.sync()
+            runs.append((e.weights(), e.states(), e.actions(), e.env_stats()[2], e.stats()))
+    # deterministic reduction order: bit-identical run to run
+    assert (runs[0][0] == runs[1][0]).all() and (runs[0][1] == runs[1][1]).all() and (runs[0][3] == runs[1][3]).all()
+    W, S, A, H, st = runs[0]
+    assert st["total_steps"] == 65536 * 300 and st["nonfinite"] == 0
+    assert (S[:, 0] >= -1.2).all() and (S[:, 0] <= 0.6).all() and (np.abs(S[:, 1]) <= 0.07).all()
+    assert ((A >= 0) & (A < 3)).all() and np.isfinite(W).all() and np.abs(W).max() > 0
+    # the first 512 envs of the same job on the oracle (MEAN scale uses the global env count) agree for one step
+    sub = cfg.copy(n_envs=512, n_envs_global=65536)
+    with E.Engine(sub) as e:
+        o = oracle.Engine(sub)
+        e.step(1)
+        o.step(1)
+        e.sync()
+        assert (e.actions() == o.actions()).all() and np.abs(e.states() - o.states()).max() < 1e-12
+
+
+def test_shard_invariance(E):
+    """Env shards are independent given W: running envs [0, N) on one engine or as two half shards
+    (env_offset) produces identical per-env results in PER_ENV mode (no collective on the data path)."""
+    full = _cfg2(n_envs=2048, weight_mode=abi.PER_ENV, dtype=abi.F64, update_scale=abi.SCALE_SUM)
+    with E.Engine(full) as e:
+        e.step(200)
+        e.sync()
+        S, A, W = e.states(), e.actions(), e.weights()
+    for off in (0, 1024):
+        half = full.copy(n_envs=1024, env_offset=off, n_envs_global=2048)
+        with E.Engine(half) as e:
+            e.step(200)
+            e.sync()
+            assert (e.states() == S[off:off + 1024]).all() and (e.actions() == A[off:off + 1024]).all()
+            assert (e.weights() == W[off:off + 1024]).all()
+
+
+def test_learning_happens(E):
+    """Sanity: with a usable step size the shared agent learns MountainCar (episodes get shorter)."""
+    cfg = _cfg2(n_envs=4096, lr=0.02, update_scale=abi.SCALE_MEAN, max_episode_steps=2000, dtype=abi.F32)
+    with E.Engine(cfg) as e:
+        e.step(4000)
+        e.sync()
+        first = e.stats()
+        e.step(16000)
+        e.sync()
+        n_ep, last_len, _ = e.env_stats()
+        st = e.stats()
+        assert st["terminal_episodes"] > first["terminal_episodes"]
+        assert np.median(last_len[n_ep > 0]) < 1000
+
+
+def test_unsupported_combination_fails_loudly(E):
+    with pytest.raises(abi.RsrlError) as ei:
+        E.Engine(abi.default_config(basis_order=4))
+    assert ei.value.code == abi.EUNSUPPORTED
