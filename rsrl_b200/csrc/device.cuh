@@ -39,6 +39,8 @@ template <typename R> struct RealOps;
 template <> struct RealOps<float> {
     __device__ __forceinline__ static void sincospi(float x, float* s, float* c) { sincospif(x, s, c); }
     __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    // w + c*x with the product rounded first (the reference's SGD `w = w + (lr*err) * phi` is not fused)
+    __device__ __forceinline__ static float mul_add_unfused(float c, float x, float w) { return __fadd_rn(w, __fmul_rn(c, x)); }
     __device__ __forceinline__ static float abs(float a) { return fabsf(a); }
     __device__ __forceinline__ static float lowest() { return -3.402823466e+38f; }  // magnitude only matters vs 1e-7
     __device__ __forceinline__ static float clamp1(float x) { return fmaxf(-1.0f, fminf(1.0f, x)); }
@@ -46,6 +48,7 @@ template <> struct RealOps<float> {
 template <> struct RealOps<double> {
     __device__ __forceinline__ static void sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
     __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    __device__ __forceinline__ static double mul_add_unfused(double c, double x, double w) { return __dadd_rn(w, __dmul_rn(c, x)); }
     __device__ __forceinline__ static double abs(double a) { return fabs(a); }
     __device__ __forceinline__ static double lowest() { return -1.7976931348623157e+308; }  // f64::MIN
     __device__ __forceinline__ static double clamp1(double x) { return fmax(-1.0, fmin(1.0, x)); }

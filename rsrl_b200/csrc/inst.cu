@@ -45,7 +45,7 @@ static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
 #define RSRL_COMBOS(X) X(RSRL_FOURIER, 1) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_FOURIER, 5) X(RSRL_FOURIER, 7) \
                        X(RSRL_POLYNOMIAL, 2) X(RSRL_POLYNOMIAL, 3)
 #else
-#define RSRL_COMBOS(X) X(RSRL_FOURIER, 1) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_POLYNOMIAL, 2)
+#define RSRL_COMBOS(X) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_POLYNOMIAL, 2)
 #endif
 
 #define RSRL_CAT_(a, b) a##b

@@ -58,13 +58,115 @@ __host__ __device__ constexpr bool algo_has_trace(int algo) {
     return algo == RSRL_SARSA_LAMBDA || algo == RSRL_Q_LAMBDA || algo == RSRL_TD_LAMBDA;
 }
 
+// Phases B-D for one env: behaviour action, Domain::transition, TD error under W_t.
+template <typename R>
+struct CoreOut {
+    R coef;       // scaled error multiplying phi(s) (or the trace) in the update
+    R residual;   // TD error (Response{error})
+    int act;
+    bool reset_before, terminated, nonfinite;
+};
+
+template <typename R, int DOM, int BASIS, int P, int AW, bool EXT, class EvalFn>
+__device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, EvalFn evalQ,
+                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_s, CoreOut<R>& o,
+                                         int ext_act, double ext_reward, bool ext_term, const double* ext_to) {
+    using Dom = Domain<DOM>;
+    using GB = GridBasis<R, Dom::D, P, BASIS>;
+    constexpr int D = Dom::D;
+    constexpr bool TDPRED = AW == 1;  // TD(0)/TD(lambda) state-value prediction: W is F x 1
+    o.nonfinite = false;
+    o.reset_before = false;
+
+    grid_prepare<R, Dom, P, BASIS>(s, tab_s);
+
+    // ---- B: behaviour action and Q(s_t, a_t) under W_t ----
+    R q[AW];
+    evalQ(tab_s, q);
+    if (EXT) {
+        o.act = ext_act;
+    } else if (TDPRED) {
+        PolicyParams rp = a.pol;
+        rp.policy = RSRL_RANDOM;
+        o.act = policy_sample<R, Dom::A>(rp, q, g, t, STREAM_BEHAVIOUR, o.nonfinite);
+    } else {
+        o.act = policy_sample<R, AW>(a.pol, q, g, t, STREAM_BEHAVIOUR, o.nonfinite);
+    }
+    R qsa = q[0];
+    if (!TDPRED) {
+#pragma unroll
+        for (int c = 0; c < AW; ++c) if (c == o.act) qsa = q[c];
+        if (a.algo == RSRL_Q_LAMBDA) o.reset_before = o.act != argmax_first<R, AW>(q);  // q_lambda.rs:68
+    }
+
+    // ---- C: Domain::transition ----
+    double reward;
+    if (EXT) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = ext_to[d];
+        reward = ext_reward;
+        o.terminated = ext_term;
+    } else {
+        Dom::step(s, o.act, reward, o.terminated);
+    }
+
+    // ---- D: TD error with W_t ----
+    if (o.terminated) {
+        o.residual = (R)reward - qsa;
+    } else {
+        typename GB::Tab tab_n;
+        grid_prepare<R, Dom, P, BASIS>(s, tab_n);
+        R nq[AW];
+        evalQ(tab_n, nq);
+        R target;
+        if (TDPRED) {
+            target = nq[0];
+        } else if (a.algo == RSRL_QLEARNING || a.algo == RSRL_Q_LAMBDA) {
+            find_max<R, AW>(nq, target);                                                          // q_learning.rs:59
+        } else if (a.algo == RSRL_SARSA || a.algo == RSRL_SARSA_LAMBDA) {
+            const int na = policy_sample<R, AW>(a.pol, nq, g, t, STREAM_TARGET, o.nonfinite);     // sarsa.rs:61
+            target = nq[0];
+#pragma unroll
+            for (int c = 0; c < AW; ++c) if (c == na) target = nq[c];
+        } else {                                                                                  // expected_sarsa.rs:52-56
+            R p[AW];
+            policy_probs<R, AW>(a.pol.policy, (R)a.epsilon, nq, p);
+            target = (R)0;
+#pragma unroll
+            for (int c = 0; c < AW; ++c) target = target + nq[c] * p[c];
+        }
+        o.residual = (R)reward + (R)a.gamma * target - qsa;
+    }
+    if (a.algo == RSRL_SARSA_LAMBDA || a.algo == RSRL_Q_LAMBDA) o.coef = (R)(a.alpha * a.inv_scale) * o.residual;  // bypasses SGD lr
+    else if (a.algo == RSRL_TD_LAMBDA) o.coef = (R)a.inv_scale * o.residual;                                       // td_lambda.rs:56-59
+    else if (a.algo == RSRL_EXPECTED_SARSA) o.coef = (R)a.lr_scaled * ((R)a.alpha * o.residual);                   // expected_sarsa.rs:64
+    else o.coef = (R)a.lr_scaled * o.residual;
+}
+
+// Phase F: episode bookkeeping / auto-reset (examples/q_learning.rs:37,49-51). Returns the new ep counter.
+template <class Dom>
+__device__ __forceinline__ int env_bookkeeping(const StepArgs& a, uint64_t t, int64_t i, uint64_t g, double* s, int ep,
+                                               bool terminated) {
+    ep += 1;
+    if (terminated || (a.max_ep > 0 && ep >= a.max_ep)) {
+        a.n_ep[i] += 1;
+        a.last_len[i] = ep;
+        a.len_hash[i] = a.len_hash[i] * 1000003ull + (unsigned long long)ep;
+        atomicAdd(&a.counters->episodes, 1ull);
+        if (terminated) atomicAdd(&a.counters->terminal_episodes, 1ull);
+        ep = 0;
+        fresh_state<Dom>(s, a.init_mode, a.init_lo, a.init_hi, a.pol.seed, g, t + 1);
+    }
+    return ep;
+}
+
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE, bool EXT>
 __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     using O = RealOps<R>;
     constexpr int D = Dom::D, F = GB::F, FA = F * AW;
-    constexpr bool TDPRED = AW == 1;  // TD(0)/TD(lambda) state-value prediction: W is F x 1
+    constexpr bool TDPRED = AW == 1;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int BLOCK = blockDim.x;  // <= 256; chosen by the host so that the reduce buffers fit in shared memory
@@ -95,109 +197,28 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
     };
 
     typename GB::Tab tab_s;
-    R coef = (R)0;        // scaled error that multiplies phi(s) (or the trace) in the update
-    int act = 0;
-    bool reset_before = false, terminated = false;
+    CoreOut<R> o;
+    o.coef = (R)0; o.act = 0; o.reset_before = false; o.terminated = false;
 
     if (active) {
         double s[D];
-        if (EXT) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) s[d] = a.ext_from[i * D + d];
-        } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) s[d] = a.states[i * D + d];
-        }
-        grid_prepare<R, Dom, P, BASIS>(s, tab_s);
-
-        // ---- B: behaviour action and Q(s_t, a_t) under W_t ----
-        bool nonfinite = false;
-        R q[AW];
-        R qsa;
-        evalQ(tab_s, q);
-        if (EXT) {
-            act = a.ext_actions[i];
-        } else if (TDPRED) {
-            PolicyParams rp = a.pol;
-            rp.policy = RSRL_RANDOM;
-            act = policy_sample<R, Dom::A>(rp, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
-        } else {
-            act = policy_sample<R, AW>(a.pol, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
-        }
-        qsa = TDPRED ? q[0] : q[0];
-        if (!TDPRED) {
-#pragma unroll
-            for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
-        }
-        if (!TDPRED && a.algo == RSRL_Q_LAMBDA) reset_before = act != argmax_first<R, AW>(q);  // q_lambda.rs:68
-
-        // ---- C: Domain::transition ----
-        double reward;
-        if (EXT) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) s[d] = a.ext_to[i * D + d];
-            reward = a.ext_rewards[i];
-            terminated = a.ext_term[i] != 0;
-        } else {
-            Dom::step(s, act, reward, terminated);
-        }
-
-        // ---- D: TD error with W_t ----
-        R residual;
-        if (terminated) {
-            residual = (R)reward - qsa;
-        } else {
-            typename GB::Tab tab_n;
-            grid_prepare<R, Dom, P, BASIS>(s, tab_n);
-            R nq[AW];
-            evalQ(tab_n, nq);
-            R target;
-            if (TDPRED) {
-                target = nq[0];
-            } else if (a.algo == RSRL_QLEARNING || a.algo == RSRL_Q_LAMBDA) {
-                find_max<R, AW>(nq, target);                                       // q_learning.rs:59
-            } else if (a.algo == RSRL_SARSA || a.algo == RSRL_SARSA_LAMBDA) {
-                const int na = policy_sample<R, AW>(a.pol, nq, g, a.t, STREAM_TARGET, nonfinite);  // sarsa.rs:61
-                target = nq[0];
-#pragma unroll
-                for (int c = 0; c < AW; ++c) if (c == na) target = nq[c];
-            } else {                                                               // expected_sarsa.rs:52-56
-                R p[AW];
-                policy_probs<R, AW>(a.pol.policy, (R)a.epsilon, nq, p);
-                target = (R)0;
-#pragma unroll
-                for (int c = 0; c < AW; ++c) target = target + nq[c] * p[c];
-            }
-            residual = (R)reward + (R)a.gamma * target - qsa;
-        }
-        if (a.td) static_cast<R*>(a.td)[i] = residual;
-
-        // scaled error multiplying phi(s) / the trace
-        if (a.algo == RSRL_SARSA_LAMBDA || a.algo == RSRL_Q_LAMBDA) coef = (R)(a.alpha * a.inv_scale) * residual;  // bypasses SGD lr
-        else if (a.algo == RSRL_TD_LAMBDA) coef = (R)a.inv_scale * residual;                                       // td_lambda.rs:56-59
-        else if (a.algo == RSRL_EXPECTED_SARSA) coef = (R)a.lr_scaled * ((R)a.alpha * residual);                   // expected_sarsa.rs:64
-        else coef = (R)a.lr_scaled * residual;
-
-        if (nonfinite) atomicExch(&a.counters->nonfinite, 1);
-
-        // ---- F: bookkeeping (fused loop only) ----
+        for (int d = 0; d < D; ++d) s[d] = EXT ? a.ext_from[i * D + d] : a.states[i * D + d];
+        env_core<R, DOM, BASIS, P, AW, EXT>(a, a.t, g, s, evalQ, tab_s, o, EXT ? a.ext_actions[i] : 0,
+                                            EXT ? a.ext_rewards[i] : 0.0, EXT ? a.ext_term[i] != 0 : false,
+                                            EXT ? a.ext_to + i * D : nullptr);
+        if (a.td) static_cast<R*>(a.td)[i] = o.residual;
+        if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
         if (!EXT) {
-            int ep = a.ep_steps[i] + 1;
-            if (terminated || (a.max_ep > 0 && ep >= a.max_ep)) {
-                a.n_ep[i] += 1;
-                a.last_len[i] = ep;
-                a.len_hash[i] = a.len_hash[i] * 1000003ull + (unsigned long long)ep;
-                atomicAdd(&a.counters->episodes, 1ull);
-                if (terminated) atomicAdd(&a.counters->terminal_episodes, 1ull);
-                ep = 0;
-                fresh_state<Dom>(s, a.init_mode, a.init_lo, a.init_hi, a.pol.seed, g, a.t + 1);
-            }
-            a.ep_steps[i] = ep;
-            a.actions[i] = act;
+            a.ep_steps[i] = env_bookkeeping<Dom>(a, a.t, i, g, s, a.ep_steps[i], o.terminated);
+            a.actions[i] = o.act;
 #pragma unroll
             for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
         }
     }
+    const R coef = o.coef;
+    const int act = o.act;
+    const bool reset_before = o.reset_before, terminated = o.terminated;
 
     // ---- E: update ----
     if (!traces) {
@@ -206,7 +227,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
                 R* Wm = static_cast<R*>(a.W);
                 GB::for_each(tab_s, [&](int k, R phi) {
                     const int64_t idx = (int64_t)(k * AW + (TDPRED ? 0 : act)) * N + i;
-                    Wm[idx] = O::fma(coef, phi, Wm[idx]);
+                    Wm[idx] = O::mul_add_unfused(coef, phi, Wm[idx]);
                 });
             }
         } else {
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
                     zv = trace_rule<R>(a.trace_rule, rate, zv, grad);
                     if (MODE == RSRL_PER_ENV) {
                         R* Wm = static_cast<R*>(a.W);
-                        Wm[idx] = O::fma(coef, zv, Wm[idx]);
+                        Wm[idx] = O::mul_add_unfused(coef, zv, Wm[idx]);
                     } else {
                         red[j * BLOCK + tid] = zv;
                     }
