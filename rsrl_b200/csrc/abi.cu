@@ -100,6 +100,12 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     return table[k.dtype][k.domain](k, e, st);
 }
 
+static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, int grid, int block, size_t smem, cudaStream_t st) {
+    static const persist_launch_fn table[2][3] = {{launch_persist_f32_d0, launch_persist_f32_d1, launch_persist_f32_d2},
+                                                  {launch_persist_f64_d0, launch_persist_f64_d1, launch_persist_f64_d2}};
+    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, grid, block, smem, st);
+}
+
 static int unsupported(const rsrl_config_t* c) {
     char buf[160];
     snprintf(buf, sizeof buf, "combination not built: domain=%d basis=%d order=%d dtype=%d (see DESIGN.md)", c->domain, c->basis, c->basis_order, c->dtype);
@@ -155,9 +161,15 @@ struct rsrl_engine {
     double* stage = nullptr;  // f64 staging for import/export
     size_t stage_elems = 0;
     double* init_bounds = nullptr;  // lo[4], hi[4]
-    // launch shape
+    // launch shape of the one-launch-per-step kernels
     int grid = 0, block = 0;
     size_t smem = 0;
+    // persistent K-steps-per-launch kernel (persistent.cuh)
+    bool persistent = false;
+    int pgrid = 0, pblock = 0;
+    size_t psmem = 0;
+    SyncArgs sync = {nullptr, nullptr, 0, 0};
+    size_t sync1_bytes = 0, sync2_bytes = 0;
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
@@ -184,13 +196,51 @@ static void choose_launch(rsrl_engine* e) {
         const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;
         int block = 256;
         for (;; block /= 2) {
-            const size_t bytes = (((size_t)e->FA + 3) & ~(size_t)3) * e->rsz + rows * block * e->rsz + (size_t)(e->has_trace ? 1 : e->AW) * block * e->rsz;
+            const size_t bytes = (((size_t)e->FA + 3) & ~(size_t)3) * e->rsz + rows * (block + 1) * e->rsz + (size_t)(e->has_trace ? 1 : e->AW) * block * e->rsz;
             e->smem = bytes;
             if (bytes <= 200 * 1024 || block == 32) break;
         }
         e->block = block;
     }
     e->grid = (int)((e->N + e->block - 1) / e->block);
+}
+
+// Shape of the persistent kernel: one CTA per SM (SHARED: co-resident, spins on LL flags), one env per
+// thread when the shard fits (state stays in registers), F-wide reducer lanes need block >= F.
+static void choose_persistent(rsrl_engine* e) {
+    e->persistent = false;
+    if (e->has_trace) return;  // eligibility traces stream z through the per-step kernels
+    int dev = e->cfg.device, sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) return;
+    auto round32 = [](int64_t x) { return (int)((x + 31) / 32 * 32); };
+    if (e->cfg.weight_mode == RSRL_PER_ENV) {
+        e->pblock = 128;
+        e->pgrid = (int)((e->N + e->pblock - 1) / e->pblock);
+        e->psmem = 0;
+        e->persistent = true;
+        return;
+    }
+    int grid = (int)((e->N + 127) / 128);
+    if (grid > sms) grid = sms;
+    if (grid > kMaxFan * kMaxFan) grid = kMaxFan * kMaxFan;
+    const int64_t per_cta = (e->N + grid - 1) / grid;
+    int block = round32(per_cta);
+    if (block < round32(e->F)) block = round32(e->F);
+    if (block < 64) block = 64;
+    if (block > 512) block = 512;
+    if (block < e->F) return;
+    const int FP = (int)(e->F | 1);
+    const int nseg = block / (int)e->F > 0 ? block / (int)e->F : 1;
+    const size_t elems = (((size_t)e->FA + 3) & ~(size_t)3) + (size_t)block * 4 + (size_t)block * FP + (size_t)nseg * e->FA;
+    const size_t bytes = elems * e->rsz;
+    if (bytes > 220 * 1024) return;
+    e->pgrid = grid; e->pblock = block; e->psmem = bytes;
+    int gs = 1;
+    while (gs * gs < grid) ++gs;
+    e->sync.group_size = gs;
+    e->sync.n_groups = (grid + gs - 1) / gs;
+    e->persistent = true;
 }
 
 static StepArgs make_args(rsrl_engine* e) {
@@ -274,7 +324,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -299,6 +349,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
     e->epsilon = cfg->epsilon;
     choose_launch(e);
+    choose_persistent(e);
 #define E_TRY(expr)                                                                                  \
     do {                                                                                             \
         cudaError_t e__ = (expr);                                                                    \
@@ -322,6 +373,13 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     if (cfg->weight_mode == RSRL_SHARED) {
         E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
+    }
+    if (e->persistent && cfg->weight_mode == RSRL_SHARED) {
+        const size_t wpv = e->rsz / 4;
+        e->sync1_bytes = (size_t)e->pgrid * e->FA * wpv * sizeof(uint2);
+        e->sync2_bytes = (size_t)2 * e->sync.n_groups * e->FA * wpv * sizeof(uint2);
+        E_TRY(cudaMalloc(&e->sync.stage1, e->sync1_bytes));
+        E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
@@ -355,6 +413,8 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     CU_TRY(cudaMemsetAsync(e->last_len, 0, N * sizeof(int32_t), st));
     CU_TRY(cudaMemsetAsync(e->len_hash, 0, N * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(e->counters, 0, sizeof(Counters), st));
+    if (e->sync.stage1) CU_TRY(cudaMemsetAsync(e->sync.stage1, 0, e->sync1_bytes, st));  // epoch 0 is never published
+    if (e->sync.stage2) CU_TRY(cudaMemsetAsync(e->sync.stage2, 0, e->sync2_bytes, st));
     e->t = 0;
     if (init_states) {
         CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -380,6 +440,24 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     if (!e) return fail(RSRL_EINVAL, "null engine");
     if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    if (e->persistent && e->world == 1) {
+        // K batched steps per launch; bounded so that one launch stays well under a second
+        while (k_steps > 0) {
+            const int k = (int)(k_steps < 65536 ? k_steps : 65536);
+            StepArgs a = make_args(e);
+            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->pgrid, e->pblock, e->psmem, e->stream);
+            if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
+                cudaGetLastError();
+                e->persistent = false;
+                return rsrl_engine_step(e, k_steps);
+            }
+            CU_TRY(ce);
+            e->launches += 1;
+            e->t += (uint64_t)k;
+            k_steps -= k;
+        }
+        return RSRL_OK;
+    }
     for (int64_t k = 0; k < k_steps; ++k) {
         StepArgs a = make_args(e);
         CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream));

@@ -28,6 +28,29 @@ static cudaError_t launch_mode(int mode, bool ext, const StepArgs& a, int grid, 
                : launch_one<BASIS, P, AW, RSRL_PER_ENV, false>(a, grid, block, smem, st);
 }
 
+template <int BASIS, int P, int AW, int MODE>
+static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = persistent_kernel<R, DOM, BASIS, P, AW, MODE>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    if (MODE == RSRL_SHARED && grid > 1) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
+        if (e != cudaSuccess) return e;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((long long)per_sm * sms < grid) return cudaErrorCooperativeLaunchTooLarge;
+        void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy};
+        return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st);
+    }
+    kern<<<grid, block, smem, st>>>(a, k_steps, sy);
+    return cudaGetLastError();
+}
+
 template <int BASIS, int P, int AW>
 static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
     const int block = 128;
@@ -58,6 +81,21 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
     if (k.basis == B && k.order == P) {                                                          \
         if (k.aw == A) return launch_mode<B, P, A>(mode, ext, a, grid, block, smem, st);         \
         if (k.aw == 1) return launch_mode<B, P, 1>(mode, ext, a, grid, block, smem, st);         \
+    }
+    RSRL_COMBOS(X)
+#undef X
+    return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy,
+                                                   int grid, int block, size_t smem, cudaStream_t st) {
+    constexpr int A = Domain<DOM>::A;
+#define X(B, P)                                                                                                       \
+    if (k.basis == B && k.order == P) {                                                                               \
+        if (k.aw == A) return mode == RSRL_SHARED ? persist_one<B, P, A, RSRL_SHARED>(a, k_steps, sy, grid, block, smem, st)   \
+                                                  : persist_one<B, P, A, RSRL_PER_ENV>(a, k_steps, sy, grid, block, smem, st); \
+        if (k.aw == 1) return mode == RSRL_SHARED ? persist_one<B, P, 1, RSRL_SHARED>(a, k_steps, sy, grid, block, smem, st)   \
+                                                  : persist_one<B, P, 1, RSRL_PER_ENV>(a, k_steps, sy, grid, block, smem, st); \
     }
     RSRL_COMBOS(X)
 #undef X

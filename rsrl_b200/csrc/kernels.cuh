@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
     const int BLOCK = blockDim.x;  // <= 256; chosen by the host so that the reduce buffers fit in shared memory
     R* Wsm = reinterpret_cast<R*>(smem_raw);  // FA (SHARED)
     R* red = Wsm + ((FA + 3) & ~3);           // SHARED: phiT[F][BLOCK] or zT[FA][BLOCK]
-    R* dc = red + (size_t)(algo_has_trace(a.algo) ? FA : F) * BLOCK;  // SHARED: coef[AW][BLOCK] (trace: [BLOCK])
+    const int RS = BLOCK + 1;  // padded row stride: reducer lanes (different rows, same column) hit different banks
+    R* dc = red + (size_t)(algo_has_trace(a.algo) ? FA : F) * RS;  // SHARED: coef[AW][BLOCK] (trace: [BLOCK])
 
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * BLOCK + tid;
@@ -233,10 +234,10 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
         } else {
             // CTA reduce in a fixed order: phiT[k][tid], dc[a][tid] -> thread j sums over tid
             if (active) {
-                GB::for_each(tab_s, [&](int k, R phi) { red[k * BLOCK + tid] = phi; });
+                GB::for_each(tab_s, [&](int k, R phi) { red[k * RS + tid] = phi; });
             } else {
 #pragma unroll 4
-                for (int k = 0; k < F; ++k) red[k * BLOCK + tid] = (R)0;
+                for (int k = 0; k < F; ++k) red[k * RS + tid] = (R)0;
             }
 #pragma unroll
             for (int c = 0; c < AW; ++c) dc[c * BLOCK + tid] = (active && (TDPRED || c == act)) ? coef : (R)0;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
                 const int k = j / AW, c = j % AW;
                 R acc = (R)0;
 #pragma unroll 8
-                for (int t2 = 0; t2 < BLOCK; ++t2) acc = O::fma(red[k * BLOCK + t2], dc[c * BLOCK + t2], acc);
+                for (int t2 = 0; t2 < BLOCK; ++t2) acc = O::fma(red[k * RS + t2], dc[c * BLOCK + t2], acc);
                 static_cast<R*>(a.partials)[(int64_t)blockIdx.x * FA + j] = acc;
             }
         }
@@ -267,13 +268,13 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
                         R* Wm = static_cast<R*>(a.W);
                         Wm[idx] = O::mul_add_unfused(coef, zv, Wm[idx]);
                     } else {
-                        red[j * BLOCK + tid] = zv;
+                        red[j * RS + tid] = zv;
                     }
                     Z[idx] = terminated ? (R)0 : zv;
                 }
             });
         } else if (MODE == RSRL_SHARED) {
-            for (int j = 0; j < FA; ++j) red[j * BLOCK + tid] = (R)0;
+            for (int j = 0; j < FA; ++j) red[j * RS + tid] = (R)0;
         }
         if (MODE == RSRL_SHARED) {
             dc[tid] = active ? coef : (R)0;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
             for (int j = tid; j < FA; j += BLOCK) {
                 R acc = (R)0;
 #pragma unroll 8
-                for (int t2 = 0; t2 < BLOCK; ++t2) acc = O::fma(red[j * BLOCK + t2], dc[t2], acc);
+                for (int t2 = 0; t2 < BLOCK; ++t2) acc = O::fma(red[j * RS + t2], dc[t2], acc);
                 static_cast<R*>(a.partials)[(int64_t)blockIdx.x * FA + j] = acc;
             }
         }
