@@ -100,10 +100,10 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     return table[k.dtype][k.domain](k, e, st);
 }
 
-static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, int cap, int grid, int block, size_t smem, cudaStream_t st) {
     static const persist_launch_fn table[2][3] = {{launch_persist_f32_d0, launch_persist_f32_d1, launch_persist_f32_d2},
                                                   {launch_persist_f64_d0, launch_persist_f64_d1, launch_persist_f64_d2}};
-    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, grid, block, smem, st);
+    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, cap, grid, block, smem, st);
 }
 
 static int unsupported(const rsrl_config_t* c) {
@@ -168,8 +168,9 @@ struct rsrl_engine {
     bool persistent = false;
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, nullptr, 0, 0};
+    SyncArgs sync = {nullptr, nullptr, nullptr, 0, 0};
     size_t sync1_bytes = 0, sync2_bytes = 0;
+    int pcap = 0;  // padded slot count of the CTA reduce buffers
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
@@ -230,10 +231,13 @@ static void choose_persistent(rsrl_engine* e) {
     if (block < 64) block = 64;
     if (block > 512) block = 512;
     if (block < e->F) return;
-    const int FP = (int)(e->F | 1);
+    const int vn = (int)(16 / e->rsz);
+    int cap = (block + vn - 1) / vn * vn;
+    while ((cap / vn) % 2 == 0) cap += vn;  // cap / vn odd: conflict-free 16-byte row reads (persistent.cuh)
     const int nseg = block / (int)e->F > 0 ? block / (int)e->F : 1;
-    const size_t elems = (((size_t)e->FA + 3) & ~(size_t)3) + (size_t)block * 4 + (size_t)block * FP + (size_t)nseg * e->FA;
+    const size_t elems = (((size_t)e->FA + 3) & ~(size_t)3) + (size_t)(e->F + e->AW) * cap + (size_t)nseg * e->FA;
     const size_t bytes = elems * e->rsz;
+    e->pcap = cap;
     if (bytes > 220 * 1024) return;
     e->pgrid = grid; e->pblock = block; e->psmem = bytes;
     int gs = 1;
@@ -324,7 +328,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->sync.stage3};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -375,11 +379,13 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     }
     if (e->persistent && cfg->weight_mode == RSRL_SHARED) {
-        const size_t wpv = e->rsz / 4;
-        e->sync1_bytes = (size_t)e->pgrid * e->FA * wpv * sizeof(uint2);
-        e->sync2_bytes = (size_t)2 * e->sync.n_groups * e->FA * wpv * sizeof(uint2);
+        const size_t vpl = e->cfg.dtype == RSRL_F32 ? 3 : 1;  // values per 16-byte LL line
+        const size_t nl = ((size_t)e->FA + vpl - 1) / vpl;
+        e->sync1_bytes = (size_t)e->pgrid * nl * sizeof(uint4);
+        e->sync2_bytes = (size_t)2 * e->sync.n_groups * nl * sizeof(uint4);
         E_TRY(cudaMalloc(&e->sync.stage1, e->sync1_bytes));
         E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
+        E_TRY(cudaMalloc(&e->sync.stage3, e->sync2_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
@@ -415,6 +421,7 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     CU_TRY(cudaMemsetAsync(e->counters, 0, sizeof(Counters), st));
     if (e->sync.stage1) CU_TRY(cudaMemsetAsync(e->sync.stage1, 0, e->sync1_bytes, st));  // epoch 0 is never published
     if (e->sync.stage2) CU_TRY(cudaMemsetAsync(e->sync.stage2, 0, e->sync2_bytes, st));
+    if (e->sync.stage3) CU_TRY(cudaMemsetAsync(e->sync.stage3, 0, e->sync2_bytes, st));
     e->t = 0;
     if (init_states) {
         CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -445,7 +452,7 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
         while (k_steps > 0) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
-            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->pgrid, e->pblock, e->psmem, e->stream);
+            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
             if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
                 cudaGetLastError();
                 e->persistent = false;

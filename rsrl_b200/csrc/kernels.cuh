@@ -67,10 +67,14 @@ struct CoreOut {
     bool reset_before, terminated, nonfinite;
 };
 
-template <typename R, int DOM, int BASIS, int P, int AW, bool EXT, class EvalFn>
-__device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, EvalFn evalQ,
-                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_s, CoreOut<R>& o,
-                                         int ext_act, double ext_reward, bool ext_term, const double* ext_to) {
+// evalS evaluates Q at the from-state (it may also record phi(s) rows for the update), evalN at s'.
+// have_tab_s: tab_s already holds the tables of s (carried over from the previous step's s').
+// tab_n returns the tables of s' (valid unless the transition was terminal).
+template <typename R, int DOM, int BASIS, int P, int AW, bool EXT, class EvalS, class EvalN>
+__device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, EvalS evalS, EvalN evalN,
+                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_s,
+                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_n, bool have_tab_s,
+                                         CoreOut<R>& o, int ext_act, double ext_reward, bool ext_term, const double* ext_to) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     constexpr int D = Dom::D;
@@ -78,11 +82,11 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
     o.nonfinite = false;
     o.reset_before = false;
 
-    grid_prepare<R, Dom, P, BASIS>(s, tab_s);
+    if (!have_tab_s) grid_prepare<R, Dom, P, BASIS>(s, tab_s);
 
     // ---- B: behaviour action and Q(s_t, a_t) under W_t ----
     R q[AW];
-    evalQ(tab_s, q);
+    evalS(tab_s, q);
     if (EXT) {
         o.act = ext_act;
     } else if (TDPRED) {
@@ -114,10 +118,9 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
     if (o.terminated) {
         o.residual = (R)reward - qsa;
     } else {
-        typename GB::Tab tab_n;
         grid_prepare<R, Dom, P, BASIS>(s, tab_n);
         R nq[AW];
-        evalQ(tab_n, nq);
+        evalN(tab_n, nq);
         R target;
         if (TDPRED) {
             target = nq[0];
@@ -146,9 +149,11 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
 // Phase F: episode bookkeeping / auto-reset (examples/q_learning.rs:37,49-51). Returns the new ep counter.
 template <class Dom>
 __device__ __forceinline__ int env_bookkeeping(const StepArgs& a, uint64_t t, int64_t i, uint64_t g, double* s, int ep,
-                                               bool terminated) {
+                                               bool terminated, bool* was_reset = nullptr) {
     ep += 1;
-    if (terminated || (a.max_ep > 0 && ep >= a.max_ep)) {
+    const bool ended = terminated || (a.max_ep > 0 && ep >= a.max_ep);
+    if (was_reset) *was_reset = ended;
+    if (ended) {
         a.n_ep[i] += 1;
         a.last_len[i] = ep;
         a.len_hash[i] = a.len_hash[i] * 1000003ull + (unsigned long long)ep;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
         });
     };
 
-    typename GB::Tab tab_s;
+    typename GB::Tab tab_s, tab_n;
     CoreOut<R> o;
     o.coef = (R)0; o.act = 0; o.reset_before = false; o.terminated = false;
 
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
         double s[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) s[d] = EXT ? a.ext_from[i * D + d] : a.states[i * D + d];
-        env_core<R, DOM, BASIS, P, AW, EXT>(a, a.t, g, s, evalQ, tab_s, o, EXT ? a.ext_actions[i] : 0,
+        env_core<R, DOM, BASIS, P, AW, EXT>(a, a.t, g, s, evalQ, evalQ, tab_s, tab_n, false, o, EXT ? a.ext_actions[i] : 0,
                                             EXT ? a.ext_rewards[i] : 0.0, EXT ? a.ext_term[i] != 0 : false,
                                             EXT ? a.ext_to + i * D : nullptr);
         if (a.td) static_cast<R*>(a.td)[i] = o.residual;
