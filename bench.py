@@ -75,6 +75,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def attach_peers(eng, dist, rank, world):
+    """SHARED weights across GPUs: dW is summed inside the persistent kernel through NVLink peer mailboxes
+    (cudaIpc handles gathered with torch.distributed); falls back to ncclAllReduce between per-step kernels."""
+    from rsrl_b200.abi import RsrlError
+    from rsrl_b200.engine import comm_unique_id
+    ok, handles = 1, [None] * world
+    try:
+        dist.all_gather_object(handles, eng.peer_export())
+        eng.peer_attach(handles, rank, world)
+    except RsrlError as err:
+        ok = 0
+        print(f"[bench] rank {rank}: peer attach failed ({err}); falling back to NCCL", file=sys.stderr)
+    import torch
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        return "in-kernel LL exchange over NVLink peer memory (rank-ordered sum)"
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)
+    return "ncclAllReduce(dW) per step (per-step kernels)"
+
+
 def run_reference(args, rank, world):
     """The reference's CPU implementation of the path (oracle port; rustc is unavailable),
     all host threads, bounded sample of the same workload.  Rank 0 only."""
@@ -143,10 +166,9 @@ def main():
     cfg = make_cfg(abi, dtype, N_ENVS_PER_GPU, env_offset=rank * N_ENVS_PER_GPU, n_global=n_global)
     cfg.device = local_rank
     eng = Engine(cfg)
+    exchange = "none"
     if world > 1:
-        uid = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(uid[0], rank, world)
+        exchange = attach_peers(eng, dist, rank, world)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -221,7 +243,7 @@ def main():
         "dtype": "f32 features/Q/weights + f64 physics" if dtype == abi.F32 else "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_envs_per_gpu": N_ENVS_PER_GPU, "batched_steps_per_bench_step": K_INNER,
-                   "l2": "flushed (256 MiB write) between timed steps", "exchange": "ncclAllReduce(dW) per step" if world > 1 else "none"},
+                   "l2": "flushed (256 MiB write) between timed steps", "exchange": exchange},
         "clocks": clocks,
         "e2e": {"value": env_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

@@ -176,6 +176,12 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
 /* ---- multi-GPU (one process per GPU; SHARED mode exchanges dW every step) ---- */
 int rsrl_comm_unique_id(uint8_t out[128]);                      /* ncclGetUniqueId on rank 0 */
 int rsrl_engine_comm_init(rsrl_engine_t* e, const uint8_t id[128], int rank, int world);
+/* In-kernel exchange over NVLink peer memory (preferred; world <= 8 GPUs of one box): every rank exports the
+ * cudaIpc handle of its dW mailbox, the host gathers the handles (any transport) and attaches them; from then
+ * on rsrl_engine_step keeps the persistent kernel and sums dW across GPUs inside it, in rank order.
+ * All ranks must call reset / step with the same arguments and in lockstep. */
+int rsrl_engine_peer_export(rsrl_engine_t* e, uint8_t handle_out[64]);
+int rsrl_engine_peer_attach(rsrl_engine_t* e, const uint8_t* handles /* world x 64 */, int rank, int world);
 
 /* ---- stateless component entry points (host buffers; computed on the GPU) ---- */
 /* Domain::{state_space, action_space, default} */

@@ -118,6 +118,8 @@ SYMBOLS = {
     "rsrl_engine_handle": (C.c_int, [_eng, C.c_int64, _dp, _ip, _dp, _dp, _u8p, C.c_uint64, _dp]),
     "rsrl_comm_unique_id": (C.c_int, [_u8p]),
     "rsrl_engine_comm_init": (C.c_int, [_eng, _u8p, C.c_int, C.c_int]),
+    "rsrl_engine_peer_export": (C.c_int, [_eng, _u8p]),
+    "rsrl_engine_peer_attach": (C.c_int, [_eng, _u8p, C.c_int, C.c_int]),
     "rsrl_domain_info": (C.c_int, [C.c_int32, _ip, _ip, _dp, _dp, _dp]),
     "rsrl_domain_step": (C.c_int, [C.c_int32, C.c_int64, _dp, _ip, _dp, _u8p]),
     "rsrl_domain_is_terminal": (C.c_int, [C.c_int32, C.c_int64, _dp, _u8p]),

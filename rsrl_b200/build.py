@@ -11,15 +11,23 @@ LIB = os.path.join(CSRC, "librsrl_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
-HEADERS = ["device.cuh", "kernels.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
+HEADERS = ["device.cuh", "kernels.cuh", "persistent.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
 
 
 def _units():
+    # RSRL_BUILD_DOMAINS=0 (development only) leaves the CartPole / Acrobot instantiations out for fast iteration;
+    # the default builds everything.
+    doms = {int(d) for d in os.environ.get("RSRL_BUILD_DOMAINS", "0,1,2").split(",")}
     units = [("abi.o", "abi.cu", [])]
     for rname, rtype in (("f32", "float"), ("f64", "double")):
         for dom in (0, 1, 2):
             suffix = f"{rname}_d{dom}"
-            units.append((f"inst_{suffix}.o", "inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"]))
+            defs = [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"]
+            if dom not in doms:
+                defs.append("-DRSRL_EMPTY")
+                units.append((f"inst_{suffix}_empty.o", "inst.cu", defs))
+            else:
+                units.append((f"inst_{suffix}.o", "inst.cu", defs))
     return units
 
 

@@ -4,6 +4,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,10 +101,10 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     return table[k.dtype][k.domain](k, e, st);
 }
 
-static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, int cap, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
     static const persist_launch_fn table[2][3] = {{launch_persist_f32_d0, launch_persist_f32_d1, launch_persist_f32_d2},
                                                   {launch_persist_f64_d0, launch_persist_f64_d1, launch_persist_f64_d2}};
-    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, cap, grid, block, smem, st);
+    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, pe, cap, grid, block, smem, st);
 }
 
 static int unsupported(const rsrl_config_t* c) {
@@ -158,6 +159,7 @@ struct rsrl_engine {
     unsigned long long* len_hash = nullptr;
     void *td = nullptr, *W = nullptr, *z = nullptr, *partials = nullptr, *dW = nullptr;
     Counters* counters = nullptr;
+    long long* phase_prof = nullptr;  // RSRL_B200_PHASE_PROFILE=1: per-CTA phase cycle counters (development aid)
     double* stage = nullptr;  // f64 staging for import/export
     size_t stage_elems = 0;
     double* init_bounds = nullptr;  // lo[4], hi[4]
@@ -168,7 +170,7 @@ struct rsrl_engine {
     bool persistent = false;
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, nullptr, nullptr, 0, 0};
+    SyncArgs sync = {nullptr, nullptr, 0, 0};
     size_t sync1_bytes = 0, sync2_bytes = 0;
     int pcap = 0;  // padded slot count of the CTA reduce buffers
     uint64_t t = 0;
@@ -177,6 +179,12 @@ struct rsrl_engine {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // in-kernel exchange over peer memory (persistent.cuh hop 3)
+    PeerArgs peer;
+    uint2* inbox = nullptr;      // this rank's mailbox [2][kMaxRanks][FA * WPV]
+    size_t inbox_bytes = 0;
+    void* peer_mapped[kMaxRanks] = {nullptr};
+    bool peers_attached = false;
 };
 
 static size_t wcount(const rsrl_engine* e) { return (size_t)e->FA * (e->cfg.weight_mode == RSRL_PER_ENV ? (size_t)e->N : 1); }
@@ -235,7 +243,9 @@ static void choose_persistent(rsrl_engine* e) {
     int cap = (block + vn - 1) / vn * vn;
     while ((cap / vn) % 2 == 0) cap += vn;  // cap / vn odd: conflict-free 16-byte row reads (persistent.cuh)
     const int nseg = block / (int)e->F > 0 ? block / (int)e->F : 1;
-    const size_t elems = (((size_t)e->FA + 3) & ~(size_t)3) + (size_t)(e->F + e->AW) * cap + (size_t)nseg * e->FA;
+    const size_t vpl0 = e->cfg.dtype == RSRL_F32 ? 3 : 1;
+    const size_t nlv = (((size_t)e->FA + vpl0 - 1) / vpl0) * vpl0;
+    const size_t elems = (size_t)e->F * 4 + (size_t)(e->F + e->AW) * cap + (size_t)nseg * e->FA + (2 * (size_t)kMaxFan + 1) * nlv;
     const size_t bytes = elems * e->rsz;
     e->pcap = cap;
     if (bytes > 220 * 1024) return;
@@ -251,7 +261,7 @@ static StepArgs make_args(rsrl_engine* e) {
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.states = e->states; a.actions = e->actions; a.ep_steps = e->ep_steps; a.n_ep = e->n_ep; a.last_len = e->last_len;
-    a.len_hash = e->len_hash; a.td = e->td; a.W = e->W; a.z = e->z; a.partials = e->partials; a.counters = e->counters;
+    a.len_hash = e->len_hash; a.td = e->td; a.W = e->W; a.z = e->z; a.partials = e->partials; a.counters = e->counters; a.phase_prof = e->phase_prof;
     a.n = e->N; a.env_offset = e->cfg.env_offset; a.t = e->t; a.max_ep = e->cfg.max_episode_steps;
     a.algo = e->cfg.algo; a.trace_rule = e->cfg.trace_rule; a.init_mode = e->cfg.init_mode;
     a.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed);
@@ -326,9 +336,23 @@ int rsrl_config_dims(const rsrl_config_t* c, int32_t* dim, int32_t* n_actions, i
 int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (!e) return RSRL_OK;
     cudaSetDevice(e->cfg.device);
+    if (e->phase_prof && e->t > 0) {
+        std::vector<long long> h((size_t)e->pgrid * 8);
+        cudaMemcpy(h.data(), e->phase_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const char* names[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "LL exchange (thread 0)", "wait LL (bar)",
+                                "  LL: sum segs + publish 1", "  LL: leader hop-1 gather", "  LL: leader sum + publish 2"};
+        for (int q = 0; q < 8; ++q) {
+            double sum = 0, mx = 0, mn = 1e30;
+            int cntq = 0;
+            for (int b2 = 0; b2 < e->pgrid; ++b2) { double v = (double)h[(size_t)b2 * 8 + q] / (double)e->t; if (v == 0) continue; ++cntq; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
+            fprintf(stderr, "[phase] %-28s cycles/step: mean %8.0f  min %8.0f  max %8.0f  (%d CTAs)\n", names[q], cntq ? sum / cntq : 0.0, mn, mx, cntq);
+        }
+        cudaFree(e->phase_prof);
+    }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->sync.stage3};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -344,6 +368,8 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     if (cfg->basis == RSRL_TILE_CODING) return unsupported(cfg);
     CU_TRY(cudaSetDevice(cfg->device));
     rsrl_engine* e = new rsrl_engine();
+    memset(&e->peer, 0, sizeof e->peer);
+    e->peer.world = 1;
     e->cfg = *cfg;
     e->key = key_of(cfg);
     e->D = dom_dim(cfg->domain); e->A = dom_actions(cfg->domain); e->AW = e->key.aw;
@@ -384,10 +410,16 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         e->sync1_bytes = (size_t)e->pgrid * nl * sizeof(uint4);
         e->sync2_bytes = (size_t)2 * e->sync.n_groups * nl * sizeof(uint4);
         E_TRY(cudaMalloc(&e->sync.stage1, e->sync1_bytes));
+        e->inbox_bytes = (size_t)2 * kMaxRanks * e->FA * (e->rsz / 4) * sizeof(uint2);
+        E_TRY(cudaMalloc(&e->inbox, e->inbox_bytes));
+        E_TRY(cudaMalloc(&e->peer.stage3, 2 * nl * sizeof(uint4)));
         E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
-        E_TRY(cudaMalloc(&e->sync.stage3, e->sync2_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
+    if (getenv("RSRL_B200_PHASE_PROFILE") && e->persistent) {
+        E_TRY(cudaMalloc(&e->phase_prof, (size_t)e->pgrid * 8 * sizeof(long long)));
+        E_TRY(cudaMemset(e->phase_prof, 0, (size_t)e->pgrid * 8 * sizeof(long long)));
+    }
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
     // probe that the combination is built (fails loudly instead of at the first step)
     {
@@ -421,7 +453,8 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     CU_TRY(cudaMemsetAsync(e->counters, 0, sizeof(Counters), st));
     if (e->sync.stage1) CU_TRY(cudaMemsetAsync(e->sync.stage1, 0, e->sync1_bytes, st));  // epoch 0 is never published
     if (e->sync.stage2) CU_TRY(cudaMemsetAsync(e->sync.stage2, 0, e->sync2_bytes, st));
-    if (e->sync.stage3) CU_TRY(cudaMemsetAsync(e->sync.stage3, 0, e->sync2_bytes, st));
+    if (e->inbox) CU_TRY(cudaMemsetAsync(e->inbox, 0, e->inbox_bytes, st));
+    if (e->peer.stage3) CU_TRY(cudaMemsetAsync(e->peer.stage3, 0, 2 * (((size_t)e->FA + (e->cfg.dtype == RSRL_F32 ? 3 : 1) - 1) / (e->cfg.dtype == RSRL_F32 ? 3 : 1)) * sizeof(uint4), st));
     e->t = 0;
     if (init_states) {
         CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -447,12 +480,12 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     if (!e) return fail(RSRL_EINVAL, "null engine");
     if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
     CU_TRY(cudaSetDevice(e->cfg.device));
-    if (e->persistent && e->world == 1) {
+    if (e->persistent && (e->world == 1 || e->peers_attached || e->cfg.weight_mode == RSRL_PER_ENV)) {
         // K batched steps per launch; bounded so that one launch stays well under a second
         while (k_steps > 0) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
-            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
+            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->peer, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
             if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
                 cudaGetLastError();
                 e->persistent = false;
@@ -716,6 +749,37 @@ int rsrl_engine_comm_init(rsrl_engine_t* e, const uint8_t id_bytes[128], int ran
     ncclResult_t r = g_nccl.CommInitRank(&e->comm, world, id, rank);
     if (r != ncclSuccess) return fail(RSRL_ECOMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     e->rank = rank; e->world = world;
+    return RSRL_OK;
+}
+
+int rsrl_engine_peer_export(rsrl_engine_t* e, uint8_t handle_out[64]) {
+    if (!e || !handle_out) return fail(RSRL_EINVAL, "null argument");
+    if (!e->inbox) return fail(RSRL_EINVAL, "engine has no peer mailbox (SHARED weights + persistent kernel only)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU_TRY(cudaIpcGetMemHandle(&h, e->inbox));
+    memcpy(handle_out, &h, 64);
+    return RSRL_OK;
+}
+
+int rsrl_engine_peer_attach(rsrl_engine_t* e, const uint8_t* handles, int rank, int world) {
+    if (!e || !handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(RSRL_EINVAL, "bad argument (world <= 8)");
+    if (!e->inbox) return fail(RSRL_EINVAL, "engine has no peer mailbox (SHARED weights + persistent kernel only)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { e->peer.inbox[r] = e->inbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) { cudaGetLastError(); return fail(RSRL_ECOMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(ce)); }
+        e->peer_mapped[r] = p;
+        e->peer.inbox[r] = static_cast<uint2*>(p);
+    }
+    e->peer.rank = rank; e->peer.world = world;
+    e->rank = rank; e->world = world;
+    e->peers_attached = true;
     return RSRL_OK;
 }
 

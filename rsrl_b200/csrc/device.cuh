@@ -241,8 +241,12 @@ __device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom
 #pragma unroll
     for (int d = 0; d < Dom::D; ++d) {
         if (BASIS == RSRL_FOURIER) {
-            // scaled = (v - lo) / (hi - lo) in f64 exactly like the reference, then to the compute type
-            const R xh = (R)ddiv(dsub(st[d], Dom::lo(d)), dsub(Dom::hi(d), Dom::lo(d)));
+            // scaled = (v - lo) / (hi - lo) in f64 exactly like the reference, then to the compute type.
+            // f32: the quotient is rounded to fp32 anyway, so multiply by the f64 reciprocal (error 1e-16 << 6e-8)
+            // instead of a ~20-instruction f64 division.
+            const double num = dsub(st[d], Dom::lo(d));
+            const R xh = sizeof(R) == 4 ? (R)dmul(num, 1.0 / (Dom::hi(d) - Dom::lo(d)))
+                                        : (R)ddiv(num, dsub(Dom::hi(d), Dom::lo(d)));
             R s1, c1;
             O::sincospi(xh, &s1, &c1);
             t.c[d][0] = c1;

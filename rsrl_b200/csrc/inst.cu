@@ -29,7 +29,7 @@ static cudaError_t launch_mode(int mode, bool ext, const StepArgs& a, int grid, 
 }
 
 template <int BASIS, int P, int AW, int MODE>
-static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, int cap, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
     auto kern = persistent_kernel<R, DOM, BASIS, P, AW, MODE>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -44,10 +44,10 @@ static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& s
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if ((long long)per_sm * sms < grid) return cudaErrorCooperativeLaunchTooLarge;
-        void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy, (void*)&cap};
+        void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy, (void*)&cap, (void*)&pe};
         return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st);
     }
-    kern<<<grid, block, smem, st>>>(a, k_steps, sy, cap);
+    kern<<<grid, block, smem, st>>>(a, k_steps, sy, cap, pe);
     return cudaGetLastError();
 }
 
@@ -64,7 +64,9 @@ static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
 // (basis, order) pairs built for this domain.  MountainCar (D = 2) unrolls any order up to 7;
 // the D = 4 domains are fully unrolled only up to order 3 here (Fourier(7) on Acrobot = 4096
 // features takes the tiled path).
-#if RSRL_DOM == 0
+#if defined(RSRL_EMPTY)
+#define RSRL_COMBOS(X)  // development builds: this domain is left out (RSRL_BUILD_DOMAINS)
+#elif RSRL_DOM == 0
 #define RSRL_COMBOS(X) X(RSRL_FOURIER, 1) X(RSRL_FOURIER, 2) X(RSRL_FOURIER, 3) X(RSRL_FOURIER, 5) X(RSRL_FOURIER, 7) \
                        X(RSRL_POLYNOMIAL, 2) X(RSRL_POLYNOMIAL, 3)
 #else
@@ -88,14 +90,14 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
 }
 
 cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy,
-                                                   int cap, int grid, int block, size_t smem, cudaStream_t st) {
+                                                   const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
     constexpr int A = Domain<DOM>::A;
 #define X(B, P)                                                                                                       \
     if (k.basis == B && k.order == P) {                                                                               \
-        if (k.aw == A) return mode == RSRL_SHARED ? persist_one<B, P, A, RSRL_SHARED>(a, k_steps, sy, cap, grid, block, smem, st)   \
-                                                  : persist_one<B, P, A, RSRL_PER_ENV>(a, k_steps, sy, cap, grid, block, smem, st); \
-        if (k.aw == 1) return mode == RSRL_SHARED ? persist_one<B, P, 1, RSRL_SHARED>(a, k_steps, sy, cap, grid, block, smem, st)   \
-                                                  : persist_one<B, P, 1, RSRL_PER_ENV>(a, k_steps, sy, cap, grid, block, smem, st); \
+        if (k.aw == A) return mode == RSRL_SHARED ? persist_one<B, P, A, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)   \
+                                                  : persist_one<B, P, A, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st); \
+        if (k.aw == 1) return mode == RSRL_SHARED ? persist_one<B, P, 1, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)   \
+                                                  : persist_one<B, P, 1, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st); \
     }
     RSRL_COMBOS(X)
 #undef X

@@ -38,6 +38,7 @@ struct StepArgs {
     void* z;         // traces R[F*AW][N] or nullptr
     void* partials;  // SHARED: R[grid][F*AW]
     Counters* counters;
+    long long* phase_prof;  // optional [grid][8] cycle counters (RSRL_B200_PHASE_PROFILE=1), else nullptr
     // external transitions (Handler::handle entry point); nullptr for the fused loop
     const double* ext_from;
     const int32_t* ext_actions;

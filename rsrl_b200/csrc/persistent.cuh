@@ -10,14 +10,17 @@
 //            they evaluate Q(s_t), and their scaled TD error per action column; (feature, segment)
 //            reducer threads then sum 4 slots per LDS.128 in slot order.
 //   hop 1  : every CTA publishes its partial as 16-byte LL lines {3 payload words, epoch}; the leader
-//            of each group of ~sqrt(G) CTAs spins on its members' lines and sums them in CTA order.
-//   hop 2  : leaders exchange group partials all-to-all (parity double-buffered), sum in group order.
-//   hop 3  : each leader publishes the total; its members spin on one line set and update their W copy.
+//            of each group of ~sqrt(G) CTAs collects its members' lines — one line per thread, so all
+//            L2 round trips overlap — and sums them in CTA order through shared memory.
+//   hop 2  : leaders publish the group partials (parity double-buffered); every CTA collects all of
+//            them (again one line per thread), sums in group order and updates its W copy.
+//            (Private per-destination mailboxes were tried: the 5 K strong stores per leader cost
+//            3 K cycles, more than the shared lines' polling contention.)
 //
-// No atomics, no fences, no grid.sync(): three LL hops per step, and only ~16K 16-byte polls in
-// flight chip-wide (the first version polled 192K 8-byte words from every CTA and saturated L2:
-// profiles/r01_persistent_v1.md).  Launched with cudaLaunchCooperativeKernel so that all CTAs
-// are co-resident (the spins need it).
+// No atomics, no fences, no grid.sync(): two LL hops per step with ~64 K 16-byte polls in flight
+// chip-wide.  (v2 polled 192 K 8-byte words with 12-16 dependent polls per thread and spent 4.7 us
+// per step in the exchange: profiles/r01_persistent_v1.md.)  Launched with
+// cudaLaunchCooperativeKernel so that all CTAs are co-resident (the spins need it).
 #pragma once
 #include "kernels.cuh"
 
@@ -28,18 +31,35 @@ constexpr int kMaxFan = 16;  // max CTAs per group and max groups (G <= 256)
 struct SyncArgs {
     uint4* stage1;  // [G][NL]             member partials
     uint4* stage2;  // [2][n_groups][NL]   group partials (parity)
-    uint4* stage3;  // [2][n_groups][NL]   totals (parity)
     int group_size;
     int n_groups;
 };
 
+// Cross-GPU exchange (one process per GPU): every rank owns an inbox of 8-byte LL words
+// {payload, epoch} that its peers write through NVLink (cudaIpc-mapped pointers).
+constexpr int kMaxRanks = 8;
+struct PeerArgs {
+    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][FA * WPV] as seen from this GPU
+    uint4* stage3;            // [2][NL] local broadcast of the all-GPU total (parity)
+    int rank, world;
+};
+
+__device__ __forceinline__ uint2 ld_ll8_sys(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_ll8_sys(uint2* p, uint32_t payload, uint32_t epoch) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
     uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t c, uint32_t epoch) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(epoch) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(epoch) : "memory");
 }
 
 // one 16-byte LL line carries VPL values + the epoch in the last word
@@ -49,8 +69,8 @@ template <> struct LL<float> {
     __device__ __forceinline__ static void publish(uint4* line, const float* v, uint32_t epoch) {
         st_ll(line, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), epoch);
     }
-    __device__ __forceinline__ static void add(const uint4& w, float* acc) {
-        acc[0] += __uint_as_float(w.x); acc[1] += __uint_as_float(w.y); acc[2] += __uint_as_float(w.z);
+    __device__ __forceinline__ static void unpack(const uint4& w, float* out) {
+        out[0] = __uint_as_float(w.x); out[1] = __uint_as_float(w.y); out[2] = __uint_as_float(w.z);
     }
 };
 template <> struct LL<double> {
@@ -59,31 +79,23 @@ template <> struct LL<double> {
         const unsigned long long u = (unsigned long long)__double_as_longlong(v[0]);
         st_ll(line, (uint32_t)u, (uint32_t)(u >> 32), 0u, epoch);
     }
-    __device__ __forceinline__ static void add(const uint4& w, double* acc) {
-        acc[0] += __longlong_as_double((long long)(((unsigned long long)w.y << 32) | w.x));
+    __device__ __forceinline__ static void unpack(const uint4& w, double* out) {
+        out[0] = __longlong_as_double((long long)(((unsigned long long)w.y << 32) | w.x));
     }
 };
 
-// acc = sum over m = 0..cnt-1 (ascending) of the LL line at line0 + m * stride.  Loads are issued
-// four at a time before their flags are checked so the L2 round trips overlap.
+// sum of rows[m * stride], m = 0..cnt-1 ascending; loads issued four at a time (latency overlap), fixed association
 template <typename R>
-__device__ __forceinline__ void ll_gather_sum(const uint4* line0, size_t stride, int cnt, uint32_t epoch, R* acc) {
-    using L = LL<R>;
-#pragma unroll
-    for (int v = 0; v < L::VPL; ++v) acc[v] = (R)0;
-    for (int m0 = 0; m0 < cnt; m0 += 4) {
-        uint4 w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (m0 + u < cnt) w[u] = ld_ll(line0 + (size_t)(m0 + u) * stride);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (m0 + u < cnt) {
-                while (w[u].w != epoch) w[u] = ld_ll(line0 + (size_t)(m0 + u) * stride);
-                L::add(w[u], acc);
-            }
-        }
+__device__ __forceinline__ R sum_rows(const R* rows, int stride, int cnt) {
+    R acc = (R)0;
+    int m = 0;
+    for (; m + 4 <= cnt; m += 4) {
+        const R v0 = rows[(size_t)(m + 0) * stride], v1 = rows[(size_t)(m + 1) * stride];
+        const R v2 = rows[(size_t)(m + 2) * stride], v3 = rows[(size_t)(m + 3) * stride];
+        acc = (((acc + v0) + v1) + v2) + v3;
     }
+    for (; m < cnt; ++m) acc += rows[(size_t)m * stride];
+    return acc;
 }
 
 template <typename R> struct Vec16;  // 16-byte shared-memory vector of R
@@ -93,7 +105,7 @@ __device__ __forceinline__ float vget(const float4& v, int i) { return i == 0 ? 
 __device__ __forceinline__ double vget(const double2& v, int i) { return i == 0 ? v.x : v.y; }
 
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE>
-__global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const int cap) {
+__global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const int cap, const PeerArgs pe) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     using O = RealOps<R>;
@@ -102,7 +114,8 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     typedef typename V::type vec_t;
     constexpr int D = Dom::D, F = GB::F, FA = F * AW;
     constexpr bool TDPRED = AW == 1;
-    constexpr int FApad = (FA + 3) & ~3;
+    constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
+    constexpr int FApad = F * WS;
     constexpr int NL = (FA + L::VPL - 1) / L::VPL;  // LL lines per partial
 
     const int tid = threadIdx.x, BLOCK = blockDim.x, G = gridDim.x, b = blockIdx.x;
@@ -123,9 +136,12 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const int nseg = BLOCK / F > 0 ? BLOCK / F : 1;
     const int seg_len = (((cap + nseg - 1) / nseg) + V::N - 1) / V::N * V::N;
     R* segpart = dcs + (size_t)AW * cap;      // [nseg][FA]
+    constexpr int NLV = NL * L::VPL;          // values per partial, padded to whole LL lines
+    R* stgA = segpart + (size_t)nseg * FA;    // [kMaxFan + 1][NLV] hop-1 staging (leader) + the group partial
+    R* stgB = stgA + (size_t)(kMaxFan + 1) * NLV;  // [kMaxFan][NLV] own partial, then hop-2 staging
 
     if (MODE == RSRL_SHARED) {
-        for (int j = tid; j < FA; j += BLOCK) Wsm[j] = static_cast<const R*>(a.W)[j];
+        for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
         for (int j = tid; j < (F + AW) * cap; j += BLOCK) red[j] = (R)0;
         __syncthreads();
     }
@@ -148,11 +164,14 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const bool reducer = MODE == RSRL_SHARED && tid < nseg * F;
     const int rk = tid % F, rseg = tid / F;
 
+    const bool prof = a.phase_prof != nullptr && tid == 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0, c2 = 0;
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
-        R racc[AW];
+        if (prof) c0 = clock64();
+        R racc[2][AW];
 #pragma unroll
-        for (int c = 0; c < AW; ++c) racc[c] = (R)0;
+        for (int c = 0; c < AW; ++c) racc[0][c] = racc[1][c] = (R)0;
 
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             if (!resident) {
@@ -169,27 +188,42 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
             o.coef = (R)0; o.act = 0; o.terminated = false;
             if (active) {
                 const uint64_t g = (uint64_t)(a.env_offset + i);
+                auto wrow = [&](int k, R* w) {  // W[k][0..AW): SHARED = 16-byte broadcast loads, PER_ENV = coalesced global
+                    if (MODE == RSRL_SHARED) {
+                        const vec_t* p = reinterpret_cast<const vec_t*>(Wsm + k * WS);
+                        vec_t v0 = p[0];
+                        if (V::N == 4) {
+#pragma unroll
+                            for (int c = 0; c < AW; ++c) w[c] = vget(v0, c);
+                        } else {
+                            vec_t v1 = AW > 2 ? p[1] : v0;
+#pragma unroll
+                            for (int c = 0; c < AW; ++c) w[c] = c < 2 ? vget(v0, c) : vget(v1, c - 2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < AW; ++c) w[c] = Wg[(int64_t)(k * AW + c) * N + i];
+                    }
+                };
                 auto evalS = [&](const typename GB::Tab& tab, R* q) {  // Q(s_t) and, SHARED, the phi(s_t) row
 #pragma unroll
                     for (int c = 0; c < AW; ++c) q[c] = (R)0;
                     GB::for_each(tab, [&](int k, R phi) {
                         if (MODE == RSRL_SHARED) red[k * cap + tid] = phi;
+                        R w[AW];
+                        wrow(k, w);
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) {
-                            const R w = MODE == RSRL_SHARED ? Wsm[k * AW + c] : Wg[(int64_t)(k * AW + c) * N + i];
-                            q[c] = O::fma(phi, w, q[c]);
-                        }
+                        for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, w[c], q[c]);
                     });
                 };
                 auto evalN = [&](const typename GB::Tab& tab, R* q) {
 #pragma unroll
                     for (int c = 0; c < AW; ++c) q[c] = (R)0;
                     GB::for_each(tab, [&](int k, R phi) {
+                        R w[AW];
+                        wrow(k, w);
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) {
-                            const R w = MODE == RSRL_SHARED ? Wsm[k * AW + c] : Wg[(int64_t)(k * AW + c) * N + i];
-                            q[c] = O::fma(phi, w, q[c]);
-                        }
+                        for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, w[c], q[c]);
                     });
                 };
                 env_core<R, DOM, BASIS, P, AW, false>(a, t, g, s, evalS, evalN, tab_s, tab_n, have_tab, o, 0, 0.0, false, nullptr);
@@ -214,24 +248,35 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
                 }
             }
+            if (prof) { c1 = clock64(); pc[0] += c1 - c0; c0 = c1; }
             if (MODE == RSRL_SHARED) {
 #pragma unroll
                 for (int c = 0; c < AW; ++c) dcs[c * cap + tid] = (active && (TDPRED || c == o.act)) ? o.coef : (R)0;
                 // (a slot idle in this chunk keeps a stale but finite phi row; its dcs entries are 0)
                 __syncthreads();
+                if (prof) { c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
                 if (reducer) {
                     const int s0 = rseg * seg_len;
                     const int s1 = s0 + seg_len < cap ? s0 + seg_len : cap;
                     const R* prow = red + (size_t)rk * cap;
-                    for (int slot = s0; slot < s1; slot += V::N) {
-                        const vec_t pv = *reinterpret_cast<const vec_t*>(prow + slot);
-                        vec_t dv[AW];
+                    // two interleaved accumulator sets (even / odd 16-byte groups) hide the LDS + FMA latency
+                    for (int slot = s0; slot < s1; slot += 2 * V::N) {
+                        const bool two = slot + V::N < s1;
+                        const vec_t pv0 = *reinterpret_cast<const vec_t*>(prow + slot);
+                        const vec_t pv1 = two ? *reinterpret_cast<const vec_t*>(prow + slot + V::N) : pv0;
+                        vec_t dv0[AW], dv1[AW];
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) dv[c] = *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot);
+                        for (int c = 0; c < AW; ++c) {
+                            dv0[c] = *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot);
+                            dv1[c] = two ? *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot + V::N) : dv0[c];
+                        }
 #pragma unroll
                         for (int u = 0; u < V::N; ++u) {
 #pragma unroll
-                            for (int c = 0; c < AW; ++c) racc[c] = O::fma(vget(pv, u), vget(dv[c], u), racc[c]);
+                            for (int c = 0; c < AW; ++c) {
+                                racc[0][c] = O::fma(vget(pv0, u), vget(dv0[c], u), racc[0][c]);
+                                if (two) racc[1][c] = O::fma(vget(pv1, u), vget(dv1[c], u), racc[1][c]);
+                            }
                         }
                     }
                 }
@@ -242,48 +287,115 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         if (MODE == RSRL_SHARED) {
             if (reducer) {
 #pragma unroll
-                for (int c = 0; c < AW; ++c) segpart[rseg * FA + rk * AW + c] = racc[c];
+                for (int c = 0; c < AW; ++c) segpart[rseg * FA + rk * AW + c] = racc[0][c] + racc[1][c];
             }
             __syncthreads();
-            for (int j = tid; j < NL; j += BLOCK) {
-                R mine[L::VPL], dW[L::VPL];
-#pragma unroll
-                for (int v = 0; v < L::VPL; ++v) {
-                    const int idx = j * L::VPL + v;
-                    R m = (R)0;
-                    if (idx < FA)
-                        for (int sg = 0; sg < nseg; ++sg) m += segpart[sg * FA + idx];
-                    mine[v] = m;
-                    dW[v] = m;
+            if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
+            const uint32_t epoch = (uint32_t)(t + 1);
+            const int par = (int)(t & 1);
+            const int grp = b / sy.group_size;
+            // this CTA's partial: segment-order sum, loads issued four at a time so their latencies overlap
+            for (int idx = tid; idx < NLV; idx += BLOCK) {
+                R m = (R)0;
+                if (idx < FA) {
+                    int sg = 0;
+                    for (; sg + 4 <= nseg; sg += 4) {
+                        const R v0 = segpart[(sg + 0) * FA + idx], v1 = segpart[(sg + 1) * FA + idx];
+                        const R v2 = segpart[(sg + 2) * FA + idx], v3 = segpart[(sg + 3) * FA + idx];
+                        m = (((m + v0) + v1) + v2) + v3;
+                    }
+                    for (; sg < nseg; ++sg) m += segpart[sg * FA + idx];
                 }
-                if (G > 1) {
-                    const uint32_t epoch = (uint32_t)(t + 1);
-                    const int par = (int)(t & 1);
-                    const int grp = b / sy.group_size;
-                    const size_t pslot = ((size_t)par * sy.n_groups + grp) * NL + j;
-                    L::publish(sy.stage1 + (size_t)b * NL + j, mine, epoch);
-                    if (b % sy.group_size == 0) {
-                        const int first = grp * sy.group_size;
-                        const int cnt = G - first < sy.group_size ? G - first : sy.group_size;
-                        R gsum[L::VPL];
-                        ll_gather_sum<R>(sy.stage1 + (size_t)first * NL + j, (size_t)NL, cnt, epoch, gsum);
-                        L::publish(sy.stage2 + pslot, gsum, epoch);
-                        ll_gather_sum<R>(sy.stage2 + (size_t)par * sy.n_groups * NL + j, (size_t)NL, sy.n_groups, epoch, dW);
-                        L::publish(sy.stage3 + pslot, dW, epoch);
-                    } else {
-                        ll_gather_sum<R>(sy.stage3 + pslot, (size_t)NL, 1, epoch, dW);
+                stgB[idx] = m;
+            }
+            __syncthreads();
+            if (G > 1) {
+                // hop 1: publish the partial as LL lines
+                for (int j = tid; j < NL; j += BLOCK) L::publish(sy.stage1 + (size_t)b * NL + j, stgB + j * L::VPL, epoch);
+                if (prof) { c2 = clock64(); pc[5] += c2 - c0; }
+                if (b % sy.group_size == 0) {  // group leader (CTA-uniform branch)
+                    const int first = grp * sy.group_size;
+                    const int cnt = G - first < sy.group_size ? G - first : sy.group_size;
+                    for (int p = tid; p < cnt * NL; p += BLOCK) {  // every thread polls one line: all round trips overlap
+                        const int m = p / NL, j = p % NL;
+                        const uint4* line = sy.stage1 + (size_t)(first + m) * NL + j;
+                        uint4 w = ld_ll(line);
+                        while (w.w != epoch) w = ld_ll(line);
+                        L::unpack(w, stgA + (size_t)m * NLV + j * L::VPL);
+                    }
+                    __syncthreads();
+                    if (prof) { c1 = clock64(); pc[6] += c1 - c2; c2 = c1; }
+                    for (int idx = tid; idx < NLV; idx += BLOCK) stgA[(size_t)kMaxFan * NLV + idx] = sum_rows<R>(stgA + idx, NLV, cnt);  // CTA order
+                    __syncthreads();
+                    for (int j = tid; j < NL; j += BLOCK)
+                        L::publish(sy.stage2 + ((size_t)par * sy.n_groups + grp) * NL + j, stgA + (size_t)kMaxFan * NLV + j * L::VPL, epoch);
+                    if (prof) { c1 = clock64(); pc[7] += c1 - c2; c2 = c1; }
+                }
+                // hop 2: every CTA collects all group partials (parity double-buffered) and sums in group order
+                __syncthreads();  // everybody is done reading stgB (the hop-1 publish)
+                for (int p = tid; p < sy.n_groups * NL; p += BLOCK) {
+                    const int g2 = p / NL, j = p % NL;
+                    const uint4* line = sy.stage2 + ((size_t)par * sy.n_groups + g2) * NL + j;
+                    uint4 w = ld_ll(line);
+                    while (w.w != epoch) w = ld_ll(line);
+                    L::unpack(w, stgB + (size_t)g2 * NLV + j * L::VPL);
+                }
+                __syncthreads();
+                for (int idx = tid; idx < NLV; idx += BLOCK) stgA[idx] = idx < FA ? sum_rows<R>(stgB + idx, NLV, sy.n_groups) : (R)0;
+            } else {
+                for (int idx = tid; idx < NLV; idx += BLOCK) stgA[idx] = stgB[idx];
+            }
+            __syncthreads();  // stgA[0..NLV) = this GPU's dW
+            if (pe.world > 1) {
+                // hop 3 (NVLink): CTA 0 of every GPU writes its dW into every rank's inbox, collects the
+                // world's partials from its own inbox, sums them in rank order (=> bit-identical replicas)
+                // and broadcasts the total to the local CTAs.  The transfer is part of this kernel.
+                constexpr int WPV = sizeof(R) / 4;
+                constexpr int FAW = FA * WPV;
+                uint32_t* words = reinterpret_cast<uint32_t*>(stgB);  // [world][FAW]
+                if (b == 0) {
+                    const uint32_t* mine_w = reinterpret_cast<const uint32_t*>(stgA);
+                    for (int p = tid; p < pe.world * FAW; p += BLOCK) {
+                        const int r = p / FAW, w = p % FAW;
+                        st_ll8_sys(pe.inbox[r] + ((size_t)par * pe.world + pe.rank) * FAW + w, mine_w[w], epoch);
+                    }
+                    for (int p = tid; p < pe.world * FAW; p += BLOCK) {
+                        const int r = p / FAW, w = p % FAW;
+                        const uint2* slot = pe.inbox[pe.rank] + ((size_t)par * pe.world + r) * FAW + w;
+                        uint2 v = ld_ll8_sys(slot);
+                        while (v.y != epoch) v = ld_ll8_sys(slot);
+                        words[r * FAW + w] = v.x;
+                    }
+                    __syncthreads();
+                    for (int idx = tid; idx < FA; idx += BLOCK) {
+                        R tot = (R)0;
+                        for (int r = 0; r < pe.world; ++r) tot += reinterpret_cast<const R*>(words + (size_t)r * FAW)[idx];  // rank order
+                        stgA[idx] = tot;
+                    }
+                    __syncthreads();
+                    if (G > 1)
+                        for (int j = tid; j < NL; j += BLOCK) L::publish(pe.stage3 + (size_t)par * NL + j, stgA + j * L::VPL, epoch);
+                } else {
+                    for (int j = tid; j < NL; j += BLOCK) {
+                        const uint4* line = pe.stage3 + (size_t)par * NL + j;
+                        uint4 w = ld_ll(line);
+                        while (w.w != epoch) w = ld_ll(line);
+                        L::unpack(w, stgA + j * L::VPL);
                     }
                 }
-#pragma unroll
-                for (int v = 0; v < L::VPL; ++v) {
-                    const int idx = j * L::VPL + v;
-                    if (idx < FA) Wsm[idx] += dW[v];
-                }
+                __syncthreads();
             }
+            for (int idx = tid; idx < FA; idx += BLOCK) Wsm[(idx / AW) * WS + idx % AW] += stgA[idx];
+            if (prof) { c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
             __syncthreads();
+            if (prof) { c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
         }
     }
 
+    if (prof) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a.phase_prof[b * 8 + q] += pc[q];
+    }
     if (resident && active) {
         a.ep_steps[i] = ep;
         a.actions[i] = act;
@@ -291,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
     }
     if (MODE == RSRL_SHARED && b == 0) {
-        for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[j];
+        for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[(j / AW) * WS + j % AW];
     }
 }
 

@@ -159,6 +159,23 @@ class Engine:
         check(self.lib.rsrl_engine_comm_init(self.h, buf, rank, world))
 
 
+def _peer_export(self):
+    buf = (C.c_uint8 * 64)()
+    check(self.lib.rsrl_engine_peer_export(self.h, buf))
+    return bytes(buf)
+
+
+def _peer_attach(self, handles, rank, world):
+    blob = b"".join(bytes(h) for h in handles)
+    assert len(blob) == 64 * world
+    buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+    check(self.lib.rsrl_engine_peer_attach(self.h, buf, rank, world))
+
+
+Engine.peer_export = _peer_export
+Engine.peer_attach = _peer_attach
+
+
 def comm_unique_id():
     buf = (C.c_uint8 * 128)()
     check(abi.load().rsrl_comm_unique_id(buf))
