@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "launch.h"
+#include "tile.cuh"
 
 using namespace rsrl;
 
@@ -69,9 +70,21 @@ static int validate(const rsrl_config_t* c) {
     if (c->env_offset < 0 || c->env_offset + c->n_envs > 0xFFFFFFFFll) return fail(RSRL_EINVAL, "global env ids must fit 32 bits");
     if (!(c->epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
     if (c->basis != RSRL_TILE_CODING && (c->basis_order < 1 || c->basis_order > 7)) return fail(RSRL_EINVAL, "basis_order must be in 1..7");
+    if (c->basis == RSRL_TILE_CODING) {
+        if (c->n_tilings < 1 || c->n_tilings > kMaxTilings) return fail(RSRL_EINVAL, "n_tilings must be in 1..16");
+        if (c->tiles_per_dim < 1) return fail(RSRL_EINVAL, "tiles_per_dim must be >= 1");
+        if (c->memory_size < 2 || (c->memory_size & (c->memory_size - 1))) return fail(RSRL_EINVAL, "memory_size must be a power of two");
+    }
     if (algo_td_pred(c->algo) && c->policy != RSRL_RANDOM)
         return fail(RSRL_EINVAL, "TD(0)/TD(lambda) predict V(s): the behaviour policy must be RSRL_RANDOM");
     return RSRL_OK;
+}
+
+static int64_t n_features(const rsrl_config_t* c) {
+    return c->basis == RSRL_TILE_CODING ? c->memory_size : ipow(c->basis_order + 1, dom_dim(c->domain));
+}
+static TileParams tile_params(const rsrl_config_t* c) {
+    TileParams tp; tp.n_tilings = c->n_tilings; tp.tiles_per_dim = c->tiles_per_dim; tp.memory_mask = c->memory_size - 1; return tp;
 }
 
 static BasisKey key_of(const rsrl_config_t* c) {
@@ -168,6 +181,7 @@ struct rsrl_engine {
     size_t smem = 0;
     // persistent K-steps-per-launch kernel (persistent.cuh)
     bool persistent = false;
+    int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
     SyncArgs sync = {nullptr, nullptr, 0, 0};
@@ -176,6 +190,11 @@ struct rsrl_engine {
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
+    // TileCoding engines (tile.cuh)
+    bool tile = false;
+    TileArgs targs;
+    unsigned long long tile_steps = 0;  // batched steps (fused + handle) since reset: barrier target / table rotation
+    size_t tileG_bytes = 0;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -218,7 +237,8 @@ static void choose_launch(rsrl_engine* e) {
 // thread when the shard fits (state stays in registers), F-wide reducer lanes need block >= F.
 static void choose_persistent(rsrl_engine* e) {
     e->persistent = false;
-    if (e->has_trace) return;  // eligibility traces stream z through the per-step kernels
+    e->pmode = e->cfg.weight_mode;
+    if (e->has_trace && e->cfg.weight_mode == RSRL_PER_ENV) return;  // per-env W + traces: per-step kernels
     int dev = e->cfg.device, sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) return;
@@ -234,18 +254,23 @@ static void choose_persistent(rsrl_engine* e) {
     if (grid > sms) grid = sms;
     if (grid > kMaxFan * kMaxFan) grid = kMaxFan * kMaxFan;
     const int64_t per_cta = (e->N + grid - 1) / grid;
+    const int64_t rows = e->has_trace ? e->FA : e->F;  // traces: z (F*A rows) lives in shared memory for the whole launch
+    if (e->has_trace) {
+        if (per_cta > 512) return;  // needs one env per thread
+        e->pmode = kModeSharedTrace;
+    }
     int block = round32(per_cta);
-    if (block < round32(e->F)) block = round32(e->F);
+    if (block < round32(rows)) block = round32(rows);
     if (block < 64) block = 64;
     if (block > 512) block = 512;
-    if (block < e->F) return;
+    if (block < rows) return;
     const int vn = (int)(16 / e->rsz);
     int cap = (block + vn - 1) / vn * vn;
     while ((cap / vn) % 2 == 0) cap += vn;  // cap / vn odd: conflict-free 16-byte row reads (persistent.cuh)
-    const int nseg = block / (int)e->F > 0 ? block / (int)e->F : 1;
+    const int nseg = block / (int)rows > 0 ? block / (int)rows : 1;
     const size_t vpl0 = e->cfg.dtype == RSRL_F32 ? 3 : 1;
     const size_t nlv = (((size_t)e->FA + vpl0 - 1) / vpl0) * vpl0;
-    const size_t elems = (size_t)e->F * 4 + (size_t)(e->F + e->AW) * cap + (size_t)nseg * e->FA + (2 * (size_t)kMaxFan + 1) * nlv;
+    const size_t elems = (size_t)e->F * 4 + (size_t)(rows + (e->has_trace ? 1 : e->AW)) * cap + (size_t)nseg * e->FA + (2 * (size_t)kMaxFan + 1) * nlv;
     const size_t bytes = elems * e->rsz;
     e->pcap = cap;
     if (bytes > 220 * 1024) return;
@@ -329,7 +354,7 @@ int rsrl_config_dims(const rsrl_config_t* c, int32_t* dim, int32_t* n_actions, i
     if (rc) return rc;
     if (dim) *dim = dom_dim(c->domain);
     if (n_actions) *n_actions = dom_actions(c->domain);
-    if (n_features) *n_features = c->basis == RSRL_TILE_CODING ? c->memory_size : ipow(c->basis_order + 1, dom_dim(c->domain));
+    if (n_features) *n_features = ::n_features(c);
     return RSRL_OK;
 }
 
@@ -352,7 +377,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -365,21 +390,37 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     int rc = validate(cfg);
     if (rc) return rc;
     if ((rc = need_device())) return rc;
-    if (cfg->basis == RSRL_TILE_CODING) return unsupported(cfg);
+    if (cfg->basis == RSRL_TILE_CODING && (cfg->weight_mode != RSRL_SHARED || algo_has_trace(cfg->algo)))
+        return fail(RSRL_EUNSUPPORTED, "TileCoding is built for SHARED weights without eligibility traces");
     CU_TRY(cudaSetDevice(cfg->device));
     rsrl_engine* e = new rsrl_engine();
+    memset(&e->targs, 0, sizeof e->targs);
+    e->tile = cfg->basis == RSRL_TILE_CODING;
     memset(&e->peer, 0, sizeof e->peer);
     e->peer.world = 1;
     e->cfg = *cfg;
     e->key = key_of(cfg);
     e->D = dom_dim(cfg->domain); e->A = dom_actions(cfg->domain); e->AW = e->key.aw;
     e->N = cfg->n_envs; e->NG = cfg->n_envs_global > 0 ? cfg->n_envs_global : cfg->n_envs;
-    e->F = ipow(cfg->basis_order + 1, e->D); e->FA = e->F * e->AW;
+    e->F = n_features(cfg); e->FA = e->F * e->AW;
     e->has_trace = algo_has_trace(cfg->algo);
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
     e->epsilon = cfg->epsilon;
-    choose_launch(e);
-    choose_persistent(e);
+    if (e->tile) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        e->pgrid = (int)((e->N + 127) / 128);
+        if (e->pgrid > sms) e->pgrid = sms;
+        const int64_t per_cta = (e->N + e->pgrid - 1) / e->pgrid;
+        e->pblock = (int)((per_cta + 31) / 32 * 32);
+        if (e->pblock > 512) e->pblock = 512;
+        if (e->pblock < 64) e->pblock = 64;
+        e->psmem = (size_t)e->FA * e->rsz;
+        e->grid = 1; e->block = 64; e->smem = 0;
+    } else {
+        choose_launch(e);
+        choose_persistent(e);
+    }
 #define E_TRY(expr)                                                                                  \
     do {                                                                                             \
         cudaError_t e__ = (expr);                                                                    \
@@ -400,7 +441,13 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     if (cfg->record_td_error) E_TRY(cudaMalloc(&e->td, N * e->rsz));
     E_TRY(cudaMalloc(&e->W, wcount(e) * e->rsz));
     if (e->has_trace) E_TRY(cudaMalloc(&e->z, (size_t)e->FA * N * e->rsz));
-    if (cfg->weight_mode == RSRL_SHARED) {
+    if (e->tile) {
+        e->targs.tp = tile_params(cfg);
+        e->targs.fx_scale = cfg->dtype == RSRL_F32 ? 1099511627776.0 : 17592186044416.0;  // 2^40 / 2^44
+        e->tileG_bytes = (size_t)4 * e->FA * sizeof(unsigned long long);
+        E_TRY(cudaMalloc(&e->targs.G, e->tileG_bytes));
+        E_TRY(cudaMalloc(&e->targs.barrier, sizeof(unsigned long long)));
+    } else if (cfg->weight_mode == RSRL_SHARED) {
         E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     }
@@ -422,7 +469,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     }
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
     // probe that the combination is built (fails loudly instead of at the first step)
-    {
+    if (!e->tile) {
         StepArgs a = make_args(e);
         a.n = 0;
         cudaError_t pe = dispatch_fused(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream);
@@ -454,6 +501,11 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     if (e->sync.stage1) CU_TRY(cudaMemsetAsync(e->sync.stage1, 0, e->sync1_bytes, st));  // epoch 0 is never published
     if (e->sync.stage2) CU_TRY(cudaMemsetAsync(e->sync.stage2, 0, e->sync2_bytes, st));
     if (e->inbox) CU_TRY(cudaMemsetAsync(e->inbox, 0, e->inbox_bytes, st));
+    if (e->tile) {
+        CU_TRY(cudaMemsetAsync(e->targs.G, 0, e->tileG_bytes, st));
+        CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
+        e->tile_steps = 0;
+    }
     if (e->peer.stage3) CU_TRY(cudaMemsetAsync(e->peer.stage3, 0, 2 * (((size_t)e->FA + (e->cfg.dtype == RSRL_F32 ? 3 : 1) - 1) / (e->cfg.dtype == RSRL_F32 ? 3 : 1)) * sizeof(uint4), st));
     e->t = 0;
     if (init_states) {
@@ -480,12 +532,26 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     if (!e) return fail(RSRL_EINVAL, "null engine");
     if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    if (e->tile) {
+        if (e->world > 1) return fail(RSRL_EUNSUPPORTED, "TileCoding engines are single-GPU (shard envs with PER-GPU agents instead)");
+        while (k_steps > 0) {
+            const int k = (int)(k_steps < 65536 ? k_steps : 65536);
+            StepArgs a = make_args(e);
+            e->targs.barrier_base = e->tile_steps;
+            auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;
+            CU_TRY(fn(e->cfg.domain, e->AW, false, a, k, e->targs, e->pgrid, e->pblock, e->psmem, e->stream));
+            e->launches += 1;
+            e->t += (uint64_t)k; e->tile_steps += (unsigned long long)k;
+            k_steps -= k;
+        }
+        return RSRL_OK;
+    }
     if (e->persistent && (e->world == 1 || e->peers_attached || e->cfg.weight_mode == RSRL_PER_ENV)) {
         // K batched steps per launch; bounded so that one launch stays well under a second
         while (k_steps > 0) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
-            cudaError_t ce = dispatch_persist(e->key, e->cfg.weight_mode, a, k, e->sync, e->peer, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
+            cudaError_t ce = dispatch_persist(e->key, e->pmode, a, k, e->sync, e->peer, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
             if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
                 cudaGetLastError();
                 e->persistent = false;
@@ -658,7 +724,8 @@ static int engine_eval(rsrl_engine* e, int mode, int64_t n, const double* states
     ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = e->W; ea.w_env_stride = pe ? 1 : 0;
     ea.out = mode == 1 ? dout.as<double>() : nullptr; ea.act_out = mode == 1 ? nullptr : dout.as<int32_t>();
     ea.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed); ea.draw = draw; ea.env_offset = e->cfg.env_offset; ea.counters = e->counters;
-    CU_TRY(dispatch_eval(e->key, ea, e->stream));
+    if (e->tile) CU_TRY((e->cfg.dtype == RSRL_F32 ? launch_tile_eval_f32 : launch_tile_eval_f64)(e->cfg.domain, e->AW, ea, e->targs.tp, e->stream));
+    else CU_TRY(dispatch_eval(e->key, ea, e->stream));
     e->launches += 1;
     if (mode == 1) CU_TRY(cudaMemcpyAsync(q_out, dout.p, (size_t)n * e->AW * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     else CU_TRY(cudaMemcpyAsync(act_out, dout.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -704,12 +771,22 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
     a.n = n; a.t = draw; a.td = dtd.p;
     a.ext_from = dfrom.as<double>(); a.ext_to = dto.as<double>(); a.ext_actions = dact.as<int32_t>();
     a.ext_rewards = drew.as<double>(); a.ext_term = dterm.as<uint8_t>();
+    if (e->tile) {
+        e->targs.barrier_base = e->tile_steps;
+        int g2 = (int)((n + 127) / 128);
+        if (g2 > e->pgrid) g2 = e->pgrid;
+        auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;
+        CU_TRY(fn(e->cfg.domain, e->AW, true, a, 1, e->targs, g2, e->pblock, e->psmem, st));
+        e->launches += 1;
+        e->tile_steps += 1;
+    } else {
     const int grid = (int)((n + e->block - 1) / e->block);
     CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, true, a, grid, e->block, e->smem, st));
     e->launches += 1;
     if (e->cfg.weight_mode == RSRL_SHARED) {
         int rc = finish_shared_step(e, grid);
         if (rc) return rc;
+    }
     }
     if (td_out) {
         int rc = ensure_stage(e, (size_t)n);
@@ -841,11 +918,10 @@ static int stateless_eval(const rsrl_config_t* cfg, int mode, int64_t n, const d
     if (rc) return rc;
     if (n <= 0 || !states || !out) return fail(RSRL_EINVAL, "bad argument");
     if ((rc = need_device())) return rc;
-    if (cfg->basis == RSRL_TILE_CODING) return unsupported(cfg);
     BasisKey k = key_of(cfg);
     k.aw = aw;
     const int D = dom_dim(cfg->domain);
-    const int64_t F = ipow(cfg->basis_order + 1, D);
+    const int64_t F = n_features(cfg);
     const size_t rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
     const size_t out_elems = (size_t)n * (mode == 0 ? F : aw);
     DevBuf ds, dw, dwr, dout;
@@ -862,7 +938,10 @@ static int stateless_eval(const rsrl_config_t* cfg, int mode, int64_t n, const d
     EvalArgs ea;
     memset(&ea, 0, sizeof ea);
     ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = dwr.p; ea.out = dout.as<double>();
-    cudaError_t ce = dispatch_eval(k, ea, 0);
+    if (mode == 0 && cfg->basis == RSRL_TILE_CODING) CU_TRY(cudaMemset(dout.p, 0, out_elems * sizeof(double)));
+    cudaError_t ce = cfg->basis == RSRL_TILE_CODING
+                         ? (cfg->dtype == RSRL_F32 ? launch_tile_eval_f32 : launch_tile_eval_f64)(cfg->domain, aw, ea, tile_params(cfg), 0)
+                         : dispatch_eval(k, ea, 0);
     if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(cfg); }
     CU_TRY(ce);
     CU_TRY(cudaMemcpy(out, dout.p, out_elems * sizeof(double), cudaMemcpyDeviceToHost));

@@ -349,6 +349,57 @@ struct GridBasis {
 };
 
 // ---------------------------------------------------------------------------
+// TileCoding (project-defined spec, identical to oracle/rsrl_oracle.c:orc_tile_indices; the lfa crate's
+// hasher is a user-supplied BuildHasher, so there is no reference behaviour to match):
+//   x^ = (x - lo) / (hi - lo);  q_d = floor(x^_d * P * T);  tiling t: coord_d = (q_d + t*(1+2d)) / T;
+//   row = fmix32(FNV-style combine(t, coord)) & (M - 1);  active set = unique rows, activation 1.0.
+// Integer work: bit-exact with the oracle.
+// ---------------------------------------------------------------------------
+constexpr int kMaxTilings = 16;
+struct TileTab {
+    int32_t idx[kMaxTilings];  // unique active rows, idx[0..n)
+    int n;
+};
+struct TileParams {
+    int n_tilings, tiles_per_dim, memory_mask;
+};
+
+__device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* coord, int D) {
+    uint32_t h = (tiling + 1u) * 0x9E3779B1u;
+    for (int d = 0; d < D; ++d) h = (h ^ (uint32_t)coord[d]) * 0x85EBCA6Bu;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+template <class Dom>
+__device__ __forceinline__ void tile_prepare(const double* st, const TileParams& tp, TileTab& tab) {
+    int32_t q[Dom::D];
+#pragma unroll
+    for (int d = 0; d < Dom::D; ++d) {
+        const double xh = ddiv(dsub(st[d], Dom::lo(d)), dsub(Dom::hi(d), Dom::lo(d)));
+        q[d] = (int32_t)floor(dmul(dmul(xh, (double)tp.tiles_per_dim), (double)tp.n_tilings));
+    }
+    tab.n = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxTilings; ++t) {
+        if (t < tp.n_tilings) {
+            int32_t coord[Dom::D];
+#pragma unroll
+            for (int d = 0; d < Dom::D; ++d) coord[d] = (q[d] + t * (1 + 2 * d)) / tp.n_tilings;
+            const int32_t row = (int32_t)(tile_hash((uint32_t)t, coord, Dom::D) & (uint32_t)tp.memory_mask);
+            bool dup = false;
+#pragma unroll
+            for (int j = 0; j < kMaxTilings; ++j) dup |= (j < tab.n) && tab.idx[j] == row;
+            if (!dup) {
+#pragma unroll
+                for (int j = 0; j < kMaxTilings; ++j) if (j == tab.n) tab.idx[j] = row;  // register-friendly insert
+                tab.n += 1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // argmax family + policies
 // ---------------------------------------------------------------------------
 // utils.rs:6-21 argmaxima: returns the tie set as a bit mask; a value within 1e-7 of `max` joins

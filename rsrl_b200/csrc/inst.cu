@@ -37,7 +37,7 @@ static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& s
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    if (MODE == RSRL_SHARED && grid > 1) {
+    if (MODE != RSRL_PER_ENV && grid > 1) {
         int per_sm = 0, dev = 0, sms = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
         if (e != cudaSuccess) return e;
@@ -92,12 +92,14 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
 cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy,
                                                    const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
     constexpr int A = Domain<DOM>::A;
-#define X(B, P)                                                                                                       \
-    if (k.basis == B && k.order == P) {                                                                               \
-        if (k.aw == A) return mode == RSRL_SHARED ? persist_one<B, P, A, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)   \
-                                                  : persist_one<B, P, A, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st); \
-        if (k.aw == 1) return mode == RSRL_SHARED ? persist_one<B, P, 1, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)   \
-                                                  : persist_one<B, P, 1, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st); \
+#define RSRL_PERSIST(B, P, AWV)                                                                                   \
+    (mode == RSRL_SHARED ? persist_one<B, P, AWV, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)         \
+     : mode == RSRL_PER_ENV ? persist_one<B, P, AWV, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st)     \
+                            : persist_one<B, P, AWV, kModeSharedTrace>(a, k_steps, sy, pe, cap, grid, block, smem, st))
+#define X(B, P)                                   \
+    if (k.basis == B && k.order == P) {           \
+        if (k.aw == A) return RSRL_PERSIST(B, P, A); \
+        if (k.aw == 1) return RSRL_PERSIST(B, P, 1); \
     }
     RSRL_COMBOS(X)
 #undef X

@@ -71,19 +71,18 @@ struct CoreOut {
 // evalS evaluates Q at the from-state (it may also record phi(s) rows for the update), evalN at s'.
 // have_tab_s: tab_s already holds the tables of s (carried over from the previous step's s').
 // tab_n returns the tables of s' (valid unless the transition was terminal).
-template <typename R, int DOM, int BASIS, int P, int AW, bool EXT, class EvalS, class EvalN>
-__device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, EvalS evalS, EvalN evalN,
-                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_s,
-                                         typename GridBasis<R, Domain<DOM>::D, P, BASIS>::Tab& tab_n, bool have_tab_s,
-                                         CoreOut<R>& o, int ext_act, double ext_reward, bool ext_term, const double* ext_to) {
+// prep(state, tab) builds the basis tables of a state (Fourier/Polynomial grid tables or tile rows).
+template <typename R, int DOM, int AW, bool EXT, class Tab, class Prep, class EvalS, class EvalN>
+__device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, Prep prep, EvalS evalS, EvalN evalN,
+                                         Tab& tab_s, Tab& tab_n, bool have_tab_s, CoreOut<R>& o, int ext_act, double ext_reward,
+                                         bool ext_term, const double* ext_to) {
     using Dom = Domain<DOM>;
-    using GB = GridBasis<R, Dom::D, P, BASIS>;
     constexpr int D = Dom::D;
     constexpr bool TDPRED = AW == 1;  // TD(0)/TD(lambda) state-value prediction: W is F x 1
     o.nonfinite = false;
     o.reset_before = false;
 
-    if (!have_tab_s) grid_prepare<R, Dom, P, BASIS>(s, tab_s);
+    if (!have_tab_s) prep(s, tab_s);
 
     // ---- B: behaviour action and Q(s_t, a_t) under W_t ----
     R q[AW];
@@ -119,7 +118,7 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
     if (o.terminated) {
         o.residual = (R)reward - qsa;
     } else {
-        grid_prepare<R, Dom, P, BASIS>(s, tab_n);
+        prep(s, tab_n);
         R nq[AW];
         evalN(tab_n, nq);
         R target;
@@ -211,7 +210,8 @@ __global__ void __launch_bounds__(256) fused_step_kernel(const StepArgs a) {
         double s[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) s[d] = EXT ? a.ext_from[i * D + d] : a.states[i * D + d];
-        env_core<R, DOM, BASIS, P, AW, EXT>(a, a.t, g, s, evalQ, evalQ, tab_s, tab_n, false, o, EXT ? a.ext_actions[i] : 0,
+        auto prep = [](const double* st, typename GB::Tab& tb) { grid_prepare<R, Dom, P, BASIS>(st, tb); };
+        env_core<R, DOM, AW, EXT>(a, a.t, g, s, prep, evalQ, evalQ, tab_s, tab_n, false, o, EXT ? a.ext_actions[i] : 0,
                                             EXT ? a.ext_rewards[i] : 0.0, EXT ? a.ext_term[i] != 0 : false,
                                             EXT ? a.ext_to + i * D : nullptr);
         if (a.td) static_cast<R*>(a.td)[i] = o.residual;

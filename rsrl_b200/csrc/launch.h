@@ -42,4 +42,11 @@ typedef cudaError_t (*persist_launch_fn)(const BasisKey&, int weight_mode, const
 RSRL_DECL_INST(f32_d0) RSRL_DECL_INST(f32_d1) RSRL_DECL_INST(f32_d2)
 RSRL_DECL_INST(f64_d0) RSRL_DECL_INST(f64_d1) RSRL_DECL_INST(f64_d2)
 
+struct TileArgs;
+struct TileParams;
+cudaError_t launch_tile_persist_f32(int domain, int aw, bool ext, const StepArgs&, int k, const TileArgs&, int grid, int block, size_t smem, cudaStream_t);
+cudaError_t launch_tile_persist_f64(int domain, int aw, bool ext, const StepArgs&, int k, const TileArgs&, int grid, int block, size_t smem, cudaStream_t);
+cudaError_t launch_tile_eval_f32(int domain, int aw, const EvalArgs&, const TileParams&, cudaStream_t);
+cudaError_t launch_tile_eval_f64(int domain, int aw, const EvalArgs&, const TileParams&, cudaStream_t);
+
 }  // namespace rsrl

@@ -27,6 +27,7 @@
 namespace rsrl {
 
 constexpr int kMaxFan = 16;  // max CTAs per group and max groups (G <= 256)
+constexpr int kModeSharedTrace = 2;  // internal MODE: SHARED weights + per-env traces kept in shared memory
 
 struct SyncArgs {
     uint4* stage1;  // [G][NL]             member partials
@@ -114,6 +115,10 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     typedef typename V::type vec_t;
     constexpr int D = Dom::D, F = GB::F, FA = F * AW;
     constexpr bool TDPRED = AW == 1;
+    constexpr bool SHAREDW = MODE != RSRL_PER_ENV;          // one replicated W, dW reduced over the grid
+    constexpr bool TRACE = MODE == kModeSharedTrace;        // eligibility traces resident in shared memory
+    constexpr int ROWS = TRACE ? FA : F;                    // rows of the reduce buffer: z (F*A) or phi(s_t) (F)
+    constexpr int NDC = TRACE ? 1 : AW;                     // rows of scaled TD errors
     constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
     constexpr int FApad = F * WS;
     constexpr int NL = (FA + L::VPL - 1) / L::VPL;  // LL lines per partial
@@ -131,18 +136,18 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     // bank groups.  Rows of slots >= BLOCK are zero and stay zero.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Wsm = reinterpret_cast<R*>(smem_raw);  // [FApad]
-    R* red = Wsm + FApad;                     // [F][cap]   phi(s_t), feature-major
-    R* dcs = red + (size_t)F * cap;           // [AW][cap]  scaled TD error in the action's row, 0 elsewhere
-    const int nseg = BLOCK / F > 0 ? BLOCK / F : 1;
+    R* red = Wsm + FApad;                     // [ROWS][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
+    R* dcs = red + (size_t)ROWS * cap;        // [NDC][cap]  scaled TD error in the action's row, 0 elsewhere
+    const int nseg = BLOCK / ROWS > 0 ? BLOCK / ROWS : 1;
     const int seg_len = (((cap + nseg - 1) / nseg) + V::N - 1) / V::N * V::N;
-    R* segpart = dcs + (size_t)AW * cap;      // [nseg][FA]
+    R* segpart = dcs + (size_t)NDC * cap;     // [nseg][FA]
     constexpr int NLV = NL * L::VPL;          // values per partial, padded to whole LL lines
     R* stgA = segpart + (size_t)nseg * FA;    // [kMaxFan + 1][NLV] hop-1 staging (leader) + the group partial
     R* stgB = stgA + (size_t)(kMaxFan + 1) * NLV;  // [kMaxFan][NLV] own partial, then hop-2 staging
 
-    if (MODE == RSRL_SHARED) {
+    if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
-        for (int j = tid; j < (F + AW) * cap; j += BLOCK) red[j] = (R)0;
+        for (int j = tid; j < (ROWS + NDC) * cap; j += BLOCK) red[j] = (R)0;
         __syncthreads();
     }
     const R* Wg = static_cast<const R*>(a.W);
@@ -157,21 +162,25 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         for (int d = 0; d < D; ++d) s[d] = a.states[i * D + d];
         ep = a.ep_steps[i];
     }
+    if (TRACE && active) {  // this env's trace column: HBM -> shared memory once per launch
+        const R* Z = static_cast<const R*>(a.z);
+        for (int j = 0; j < FA; ++j) red[(size_t)j * cap + tid] = Z[(int64_t)j * N + i];
+    }
     typename GB::Tab tab_s, tab_n;
     bool have_tab = false;  // tab_s holds the tables of s (carried from the previous step's s')
 
     // reducer role: (seg, k) sums phi[k][slot] * dcs[:][slot] over its slots
-    const bool reducer = MODE == RSRL_SHARED && tid < nseg * F;
-    const int rk = tid % F, rseg = tid / F;
+    const bool reducer = SHAREDW && tid < nseg * ROWS;
+    const int rk = tid % ROWS, rseg = tid / ROWS;
 
     const bool prof = a.phase_prof != nullptr && tid == 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0, c2 = 0;
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
         if (prof) c0 = clock64();
-        R racc[2][AW];
+        R racc[2][NDC];
 #pragma unroll
-        for (int c = 0; c < AW; ++c) racc[0][c] = racc[1][c] = (R)0;
+        for (int c = 0; c < NDC; ++c) racc[0][c] = racc[1][c] = (R)0;
 
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             if (!resident) {
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
             if (active) {
                 const uint64_t g = (uint64_t)(a.env_offset + i);
                 auto wrow = [&](int k, R* w) {  // W[k][0..AW): SHARED = 16-byte broadcast loads, PER_ENV = coalesced global
-                    if (MODE == RSRL_SHARED) {
+                    if (SHAREDW) {
                         const vec_t* p = reinterpret_cast<const vec_t*>(Wsm + k * WS);
                         vec_t v0 = p[0];
                         if (V::N == 4) {
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
                     for (int c = 0; c < AW; ++c) q[c] = (R)0;
                     GB::for_each(tab, [&](int k, R phi) {
-                        if (MODE == RSRL_SHARED) red[k * cap + tid] = phi;
+                        if (SHAREDW && !TRACE) red[k * cap + tid] = phi;
                         R w[AW];
                         wrow(k, w);
 #pragma unroll
@@ -226,7 +235,8 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, w[c], q[c]);
                     });
                 };
-                env_core<R, DOM, BASIS, P, AW, false>(a, t, g, s, evalS, evalN, tab_s, tab_n, have_tab, o, 0, 0.0, false, nullptr);
+                auto prep = [](const double* st, typename GB::Tab& tb) { grid_prepare<R, Dom, P, BASIS>(st, tb); };
+                env_core<R, DOM, AW, false>(a, t, g, s, prep, evalS, evalN, tab_s, tab_n, have_tab, o, 0, 0.0, false, nullptr);
                 if (a.td) static_cast<R*>(a.td)[i] = o.residual;
                 if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
                 if (MODE == RSRL_PER_ENV) {
@@ -234,6 +244,19 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     GB::for_each(tab_s, [&](int k, R phi) {
                         const int64_t idx = (int64_t)(k * AW + (TDPRED ? 0 : o.act)) * N + i;
                         Wm[idx] = O::mul_add_unfused(o.coef, phi, Wm[idx]);
+                    });
+                }
+                if (TRACE) {
+                    // z <- rule(rate * z + grad) on this env's column (traces.rs:127-129,196-240); the CTA reduce below
+                    // then forms sum_i coef_i * z_i; z.reset() on terminal happens after the reduce.
+                    const R rate = a.trace_rule == RSRL_TRACE_DUTCH ? (R)(a.gamma * a.lambda * (1.0 - a.alpha)) : (R)(a.gamma * a.lambda);
+                    GB::for_each(tab_s, [&](int k, R phi) {
+#pragma unroll
+                        for (int c = 0; c < AW; ++c) {
+                            R* zp = red + (size_t)(k * AW + c) * cap + tid;
+                            const R zv = o.reset_before ? (R)0 : *zp;
+                            *zp = trace_rule<R>(a.trace_rule, rate, zv, (TDPRED || c == o.act) ? phi : (R)0);
+                        }
                     });
                 }
                 bool was_reset;
@@ -249,10 +272,14 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 }
             }
             if (prof) { c1 = clock64(); pc[0] += c1 - c0; c0 = c1; }
-            if (MODE == RSRL_SHARED) {
+            if (SHAREDW) {
+                if (TRACE) {
+                    dcs[tid] = active ? o.coef : (R)0;
+                } else {
 #pragma unroll
-                for (int c = 0; c < AW; ++c) dcs[c * cap + tid] = (active && (TDPRED || c == o.act)) ? o.coef : (R)0;
-                // (a slot idle in this chunk keeps a stale but finite phi row; its dcs entries are 0)
+                    for (int c = 0; c < AW; ++c) dcs[c * cap + tid] = (active && (TDPRED || c == o.act)) ? o.coef : (R)0;
+                }
+                // (a slot idle in this chunk keeps a stale but finite row; its dcs entries are 0)
                 __syncthreads();
                 if (prof) { c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
                 if (reducer) {
@@ -264,16 +291,16 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         const bool two = slot + V::N < s1;
                         const vec_t pv0 = *reinterpret_cast<const vec_t*>(prow + slot);
                         const vec_t pv1 = two ? *reinterpret_cast<const vec_t*>(prow + slot + V::N) : pv0;
-                        vec_t dv0[AW], dv1[AW];
+                        vec_t dv0[NDC], dv1[NDC];
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) {
+                        for (int c = 0; c < NDC; ++c) {
                             dv0[c] = *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot);
                             dv1[c] = two ? *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot + V::N) : dv0[c];
                         }
 #pragma unroll
                         for (int u = 0; u < V::N; ++u) {
 #pragma unroll
-                            for (int c = 0; c < AW; ++c) {
+                            for (int c = 0; c < NDC; ++c) {
                                 racc[0][c] = O::fma(vget(pv0, u), vget(dv0[c], u), racc[0][c]);
                                 if (two) racc[1][c] = O::fma(vget(pv1, u), vget(dv1[c], u), racc[1][c]);
                             }
@@ -281,13 +308,16 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     }
                 }
                 __syncthreads();
+                if (TRACE && active && o.terminated) {  // trace.reset() (sarsa_lambda.rs:78, q_lambda.rs:81, td_lambda.rs:61)
+                    for (int j = 0; j < FA; ++j) red[(size_t)j * cap + tid] = (R)0;
+                }
             }
         }
 
-        if (MODE == RSRL_SHARED) {
+        if (SHAREDW) {
             if (reducer) {
 #pragma unroll
-                for (int c = 0; c < AW; ++c) segpart[rseg * FA + rk * AW + c] = racc[0][c] + racc[1][c];
+                for (int c = 0; c < NDC; ++c) segpart[rseg * FA + (TRACE ? rk : rk * AW + c)] = racc[0][c] + racc[1][c];
             }
             __syncthreads();
             if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
@@ -402,7 +432,11 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
         for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
     }
-    if (MODE == RSRL_SHARED && b == 0) {
+    if (TRACE && active) {
+        R* Z = static_cast<R*>(a.z);
+        for (int j = 0; j < FA; ++j) Z[(int64_t)j * N + i] = red[(size_t)j * cap + tid];
+    }
+    if (SHAREDW && b == 0) {
         for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[(j / AW) * WS + j % AW];
     }
 }

@@ -1,0 +1,161 @@
+// tile.cuh — TileCoding basis (sparse features) on the fused path: BASELINE config 3
+// (CartPole / SARSA / tile coding).  SHARED weights only.
+//
+// W is a hashed table of M rows x A columns kept in shared memory by every CTA (32 KB fp32 for
+// M = 4096, A = 2).  Q(s)[a] = sum of the T active rows; the update adds the scaled TD error to the
+// T active rows of column a_t.  Contributions of different envs collide on rows, so dW is summed
+// with 64-bit fixed-point RED atomics straight into an L2-resident table: integer addition is
+// associative, hence the result is bit-reproducible regardless of arrival order (a float atomic would
+// not be).  Four dW tables rotate by step (accumulate t, read t, idle, being cleared for t+2), one
+// counter barrier per step separates "everybody added" from "everybody reads".
+#pragma once
+#include "kernels.cuh"
+
+namespace rsrl {
+
+struct TileArgs {
+    TileParams tp;
+    int pad;
+    unsigned long long* G;        // [4][M * AW] fixed-point dW accumulators
+    unsigned long long* barrier;  // monotonically increasing arrival counter
+    unsigned long long barrier_base;  // batched steps (fused or handle) completed before this launch: barrier target
+                                      // and rotation index of the dW tables
+    double fx_scale;              // 2^40 (f32) / 2^44 (f64)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid barrier (all CTAs co-resident: cooperative launch)
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (ld_acquire_u64(counter) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename R, int DOM, int AW, bool EXT>
+__global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs a, const int k_steps, const TileArgs ta) {
+    using Dom = Domain<DOM>;
+    constexpr int D = Dom::D;
+    constexpr bool TDPRED = AW == 1;
+    const int tid = threadIdx.x, BLOCK = blockDim.x, G = gridDim.x, b = blockIdx.x;
+    const int M = ta.tp.memory_mask + 1, MA = M * AW;
+    const int64_t N = a.n;
+    const int64_t per_cta = (N + G - 1) / G;
+    const int64_t base = (int64_t)b * per_cta;
+    const int64_t end = base + per_cta < N ? base + per_cta : N;
+    const int n_chunks = (int)((per_cta + BLOCK - 1) / BLOCK);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* Wsm = reinterpret_cast<R*>(smem_raw);  // [M][AW]
+    for (int j = tid; j < MA; j += BLOCK) Wsm[j] = static_cast<const R*>(a.W)[j];
+    __syncthreads();
+
+    auto evalQ = [&](const TileTab& tab, R* q) {
+#pragma unroll
+        for (int c = 0; c < AW; ++c) q[c] = (R)0;
+#pragma unroll
+        for (int j = 0; j < kMaxTilings; ++j) {
+            if (j < tab.n) {
+#pragma unroll
+                for (int c = 0; c < AW; ++c) q[c] += Wsm[tab.idx[j] * AW + c];  // activation 1.0
+            }
+        }
+    };
+    auto prep = [&](const double* st, TileTab& tb) { tile_prepare<Dom>(st, ta.tp, tb); };
+    const double inv_fx = 1.0 / ta.fx_scale;
+
+    for (int step = 0; step < k_steps; ++step) {
+        const uint64_t t = a.t + (uint64_t)step;
+        const unsigned long long rot = ta.barrier_base + (unsigned long long)step;
+        unsigned long long* Gt = ta.G + (size_t)(rot & 3) * MA;
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int64_t i = base + (int64_t)chunk * BLOCK + tid;
+            if (i < end) {
+                const uint64_t g = (uint64_t)(a.env_offset + i);
+                double s[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) s[d] = EXT ? a.ext_from[i * D + d] : a.states[i * D + d];
+                TileTab tab_s, tab_n;
+                CoreOut<R> o;
+                env_core<R, DOM, AW, EXT>(a, t, g, s, prep, evalQ, evalQ, tab_s, tab_n, false, o, EXT ? a.ext_actions[i] : 0,
+                                          EXT ? a.ext_rewards[i] : 0.0, EXT ? a.ext_term[i] != 0 : false,
+                                          EXT ? a.ext_to + i * D : nullptr);
+                if (a.td) static_cast<R*>(a.td)[i] = o.residual;
+                if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
+                // dW[row, a_t] += coef for every active row (activation 1.0), fixed point
+                const long long fx = __double2ll_rn((double)o.coef * ta.fx_scale);
+                const int col = TDPRED ? 0 : o.act;
+#pragma unroll
+                for (int j = 0; j < kMaxTilings; ++j)
+                    if (j < tab_s.n) atomicAdd(Gt + (size_t)tab_s.idx[j] * AW + col, (unsigned long long)fx);
+                if (!EXT) {
+                    a.ep_steps[i] = env_bookkeeping<Dom>(a, t, i, g, s, a.ep_steps[i], o.terminated);
+                    a.actions[i] = o.act;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
+                }
+            }
+        }
+        if (G > 1) grid_barrier(ta.barrier, (ta.barrier_base + (unsigned long long)step + 1ull) * (unsigned long long)G);
+        else { __threadfence(); __syncthreads(); }
+        // every CTA applies the same dW to its W copy; the table for step t+2 is cleared cooperatively
+        unsigned long long* Gz = ta.G + (size_t)((rot + 2) & 3) * MA;
+        for (int j = tid; j < MA; j += BLOCK) {
+            const long long v = (long long)__ldcg(Gt + j);
+            Wsm[j] += (R)((double)v * inv_fx);
+        }
+        for (int j = b * BLOCK + tid; j < MA; j += G * BLOCK) Gz[j] = 0ull;
+        __syncthreads();
+    }
+    if (b == 0)
+        for (int j = tid; j < MA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[j];
+}
+
+// component entry points for the tile basis: mode 0 dense features (N x M), 1 Q, 2 sample, 3 find_max
+template <typename R, int DOM, int AW>
+__global__ void tile_eval_kernel(int mode, int64_t n, const double* __restrict__ states, const R* __restrict__ W, TileParams tp,
+                                 double* __restrict__ out, int32_t* __restrict__ act_out, PolicyParams pol, uint64_t draw,
+                                 int64_t env_offset, Counters* counters) {
+    using Dom = Domain<DOM>;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[Dom::D];
+#pragma unroll
+    for (int d = 0; d < Dom::D; ++d) s[d] = states[i * Dom::D + d];
+    TileTab tab;
+    tile_prepare<Dom>(s, tp, tab);
+    const int M = tp.memory_mask + 1;
+    if (mode == 0) {
+        for (int j = 0; j < tab.n; ++j) out[i * M + tab.idx[j]] = 1.0;  // `out` is zero-filled by the host
+        return;
+    }
+    R q[AW];
+#pragma unroll
+    for (int c = 0; c < AW; ++c) q[c] = (R)0;
+    for (int j = 0; j < tab.n; ++j) {
+#pragma unroll
+        for (int c = 0; c < AW; ++c) q[c] += W[tab.idx[j] * AW + c];
+    }
+    if (mode == 1) {
+#pragma unroll
+        for (int c = 0; c < AW; ++c) out[i * AW + c] = (double)q[c];
+    } else if (mode == 2) {
+        bool nf = false;
+        act_out[i] = policy_sample<R, AW>(pol, q, (uint64_t)(env_offset + i), draw, STREAM_BEHAVIOUR, nf);
+        if (nf) atomicExch(&counters->nonfinite, 1);
+    } else {
+        R mx;
+        act_out[i] = find_max<R, AW>(q, mx);
+    }
+}
+
+}  // namespace rsrl

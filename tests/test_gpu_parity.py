@@ -456,3 +456,75 @@ def test_unsupported_combination_fails_loudly(E):
     with pytest.raises(abi.RsrlError) as ei:
         E.Engine(abi.default_config(basis_order=4))
     assert ei.value.code == abi.EUNSUPPORTED
+
+
+# ---------------------------------------------------------------------------------------------
+# TileCoding (BASELINE config 3: CartPole / SARSA / tile coding) — project-defined spec, integer work bit-exact
+# ---------------------------------------------------------------------------------------------
+def _tile_cfg(domain=CP, **kw):
+    base = dict(domain=domain, basis=abi.TILE_CODING, n_tilings=8, tiles_per_dim=8, memory_size=4096, algo=abi.SARSA,
+                policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=0.1 / 8, dtype=abi.F64, n_envs=65,
+                init_mode=abi.INIT_UNIFORM, init_lo=[-0.05] * 4, init_hi=[0.05] * 4, max_episode_steps=500, seed=13,
+                update_scale=abi.SCALE_MEAN, record_td_error=1)
+    base.update(kw)
+    return abi.default_config(**base)
+
+
+@pytest.mark.parametrize("domain", [MC, CP, AC])
+def test_tile_rows_bit_exact(E, oracle, domain):
+    cfg = _tile_cfg(domain=domain, n_tilings=8 if domain != MC else 16, memory_size=1024)
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(1)
+    s = rng.uniform(lo, hi, size=(400, len(lo)))
+    s[0], s[1] = lo, hi
+    got, want = E.basis_project(cfg, s), oracle.project(cfg, s)
+    assert (got == want).all()
+    assert (got.sum(axis=1) <= cfg.n_tilings).all() and (got.sum(axis=1) >= 1).all()
+    W = rng.normal(size=(1024, oracle.domain_dims(domain)[1]))
+    assert np.abs(E.lfa_evaluate(cfg, W, s) - oracle.evaluate(cfg, W, s)).max() < 1e-12
+
+
+@pytest.mark.parametrize("algo", [abi.SARSA, abi.QLEARNING, abi.EXPECTED_SARSA])
+def test_tile_engine_free_run_f64(E, oracle, algo):
+    cfg = _tile_cfg(algo=algo, alpha=1.0)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        for chunk in (1, 9, 290):
+            e.step(chunk)
+            o.step(chunk)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9, s_tol=1e-9)  # dW is summed in 2^-44 fixed point on the device
+        assert o.stats()["total_episodes"] > 0
+
+
+def test_tile_handle_and_policy_entry_points(E, oracle):
+    cfg = _tile_cfg(n_envs=200)
+    rng = np.random.default_rng(3)
+    lo, hi = oracle.domain_limits(CP)
+    s = rng.uniform(lo, hi, size=(200, 4)) * 0.5
+    a = rng.integers(0, 2, 200).astype(np.int32)
+    ns, r, term = oracle.domain_step(CP, s, a)
+    W = rng.normal(size=(4096, 2))
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.set_weights(W)
+        o.set_weights(W)
+        assert np.abs(e.evaluate(s) - oracle.evaluate(cfg, W, s)).max() < 1e-12
+        assert (e.sample(s, draw=4) == oracle.policy_sample_batch(cfg.policy, cfg.epsilon, cfg.seed, 4, 0, oracle.evaluate(cfg, W, s))).all()
+        td_e, td_o = e.handle(s, a, r, ns, term, draw_idx=2), o.handle(s, a, r, ns, term, draw_idx=2)
+        assert np.abs(td_e - td_o).max() < 1e-12 and np.abs(e.weights() - o.weights()).max() < 1e-11
+
+
+def test_cfg3_full_size_properties(E):
+    cfg = _tile_cfg(n_envs=262144, dtype=abi.F32, record_td_error=0, seed=0)
+    outs = []
+    for _ in range(2):
+        with E.Engine(cfg) as e:
+            e.step(120)
+            e.sync()
+            outs.append((e.weights(), e.states(), e.env_stats()[2], e.stats()))
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all() and (outs[0][2] == outs[1][2]).all()
+    W, S, H, st = outs[0]
+    assert st["total_steps"] == 262144 * 120 and st["nonfinite"] == 0 and st["total_episodes"] > 0
+    assert np.isfinite(W).all() and np.abs(W).max() > 0
+    assert (np.abs(S[:, 0]) <= 2.4).all() and (np.abs(S[:, 2]) <= np.pi / 15).all()

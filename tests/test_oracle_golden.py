@@ -196,3 +196,25 @@ def test_default_config_is_the_q_learning_example(oracle):
     cfg = abi.default_config()
     assert oracle.n_features(cfg) == 36 and oracle.domain_dims(cfg.domain) == (2, 3)
     assert (cfg.lr, cfg.gamma, cfg.policy, cfg.algo, cfg.seed) == (0.001, 0.9, abi.GREEDY, abi.QLEARNING, 0)
+
+
+# ---- TileCoding: project-defined spec; structural properties only ----
+def test_tile_coding_structure(oracle):
+    cfg = abi.default_config(domain=CP, basis=abi.TILE_CODING, n_tilings=8, tiles_per_dim=8, memory_size=4096)
+    lo, hi = oracle.domain_limits(CP)
+    rng = np.random.default_rng(0)
+    s = rng.uniform(lo, hi, size=(200, 4))
+    for x in s:
+        rows = oracle.tile_indices(cfg, x)
+        assert 1 <= len(rows) <= 8 and len(set(rows.tolist())) == len(rows)
+        assert ((rows >= 0) & (rows < 4096)).all()
+        assert (rows == oracle.tile_indices(cfg, x)).all()
+    # generalisation: a nearby state shares most tiles, a distant one few
+    x = (lo + hi) / 2
+    near = x + (hi - lo) * 0.004
+    far = x + (hi - lo) * 0.4
+    base = set(oracle.tile_indices(cfg, x).tolist())
+    assert len(base & set(oracle.tile_indices(cfg, near).tolist())) >= 5
+    assert len(base & set(oracle.tile_indices(cfg, far).tolist())) <= 1
+    phi = oracle.project(cfg, [x])[0]
+    assert phi.sum() == len(base) and set(np.nonzero(phi)[0].tolist()) == base

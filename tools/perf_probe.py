@@ -28,3 +28,6 @@ if __name__ == "__main__":
     run("shared f32 eps-greedy", policy=abi.EPSILON_GREEDY)
     run("shared f32 sarsa eps", policy=abi.EPSILON_GREEDY, algo=abi.SARSA)
     run("shared f32 sarsa(lambda) (per-step kernels)", policy=abi.EPSILON_GREEDY, algo=abi.SARSA_LAMBDA, k=200)
+    run("cfg5 sarsa(lambda) N=32768 (smem traces)", n_envs=32768, policy=abi.EPSILON_GREEDY, epsilon=0.2, algo=abi.SARSA_LAMBDA,
+        alpha=0.01, gamma=0.99, k=1000)
+    run("cfg5 td(lambda) N=32768 (smem traces)", n_envs=32768, policy=abi.RANDOM, algo=abi.TD_LAMBDA, gamma=0.99, k=1000)
