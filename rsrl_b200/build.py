@@ -11,7 +11,7 @@ LIB = os.path.join(CSRC, "librsrl_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
-HEADERS = ["device.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
+HEADERS = ["device.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
 
 
 def _units():
@@ -21,6 +21,7 @@ def _units():
     units = [("abi.o", "abi.cu", [])]
     for rname, rtype in (("f32", "float"), ("f64", "double")):
         units.append((f"tile_{rname}.o", "tile_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
+        units.append((f"f4_{rname}.o", "f4_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
         for dom in (0, 1, 2):
             suffix = f"{rname}_d{dom}"
             defs = [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"]

@@ -11,6 +11,7 @@
 
 #include "launch.h"
 #include "tile.cuh"
+#include "fourier4.cuh"
 
 using namespace rsrl;
 
@@ -85,6 +86,10 @@ static int64_t n_features(const rsrl_config_t* c) {
 }
 static TileParams tile_params(const rsrl_config_t* c) {
     TileParams tp; tp.n_tilings = c->n_tilings; tp.tiles_per_dim = c->tiles_per_dim; tp.memory_mask = c->memory_size - 1; return tp;
+}
+
+static bool is_f4(const rsrl_config_t* c) {
+    return c->basis == RSRL_FOURIER && dom_dim(c->domain) == 4 && (c->basis_order == 5 || c->basis_order == 7);
 }
 
 static BasisKey key_of(const rsrl_config_t* c) {
@@ -190,6 +195,10 @@ struct rsrl_engine {
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
+    // large Fourier bases on the 4-D domains (fourier4.cuh): one env kernel + one dW kernel per batched step
+    bool f4 = false;
+    F4Args f4args = {nullptr, nullptr};
+    int f4_nseg = 0;
     // TileCoding engines (tile.cuh)
     bool tile = false;
     TileArgs targs;
@@ -325,6 +334,20 @@ static int finish_shared_step(rsrl_engine* e, int n_blocks) {
     return RSRL_OK;
 }
 
+static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
+    const bool f32 = e->cfg.dtype == RSRL_F32;
+    const int grid = (int)((n + e->block - 1) / e->block);
+    cudaError_t ce = (f32 ? launch_f4_env_f32 : launch_f4_env_f64)(e->cfg.domain, e->cfg.basis_order, ext, a, e->f4args, grid, e->block, e->smem, e->stream);
+    if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(&e->cfg); }
+    CU_TRY(ce);
+    int nseg = e->f4_nseg;
+    const int64_t max_seg = (n + 63) / 64;
+    if (nseg > max_seg) nseg = (int)max_seg;
+    CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->stream));
+    e->launches += 2;
+    return finish_shared_step(e, nseg);
+}
+
 extern "C" {
 
 int rsrl_version(void) { return RSRL_ABI_VERSION; }
@@ -377,7 +400,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -396,6 +419,11 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     rsrl_engine* e = new rsrl_engine();
     memset(&e->targs, 0, sizeof e->targs);
     e->tile = cfg->basis == RSRL_TILE_CODING;
+    e->f4 = is_f4(cfg);
+    if (e->f4 && (cfg->weight_mode != RSRL_SHARED || algo_has_trace(cfg->algo) || algo_td_pred(cfg->algo))) {
+        delete e;
+        return fail(RSRL_EUNSUPPORTED, "order-5/7 Fourier bases on 4-D domains are built for SHARED weights, TD control without traces");
+    }
     memset(&e->peer, 0, sizeof e->peer);
     e->peer.world = 1;
     e->cfg = *cfg;
@@ -406,7 +434,17 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     e->has_trace = algo_has_trace(cfg->algo);
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
     e->epsilon = cfg->epsilon;
-    if (e->tile) {
+    if (e->f4) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        e->block = 128;
+        e->grid = (int)((e->N + e->block - 1) / e->block);
+        e->smem = ((size_t)e->F * 4 + (size_t)2 * cfg->basis_order * 2 * e->block) * e->rsz;
+        e->f4_nseg = (2 * sms + cfg->basis_order) / (cfg->basis_order + 1);
+        const int64_t max_seg = (e->N + 63) / 64;
+        if (e->f4_nseg > max_seg) e->f4_nseg = (int)max_seg;
+        if (e->f4_nseg < 1) e->f4_nseg = 1;
+    } else if (e->tile) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         e->pgrid = (int)((e->N + 127) / 128);
@@ -447,6 +485,11 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         e->tileG_bytes = (size_t)4 * e->FA * sizeof(unsigned long long);
         E_TRY(cudaMalloc(&e->targs.G, e->tileG_bytes));
         E_TRY(cudaMalloc(&e->targs.barrier, sizeof(unsigned long long)));
+    } else if (e->f4) {
+        E_TRY(cudaMalloc(&e->f4args.from_states, N * 4 * sizeof(double)));
+        E_TRY(cudaMalloc(&e->f4args.coef, N * e->rsz));
+        E_TRY(cudaMalloc(&e->partials, (size_t)e->f4_nseg * e->FA * e->rsz));
+        E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     } else if (cfg->weight_mode == RSRL_SHARED) {
         E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
@@ -469,7 +512,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     }
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
     // probe that the combination is built (fails loudly instead of at the first step)
-    if (!e->tile) {
+    if (!e->tile && !e->f4) {
         StepArgs a = make_args(e);
         a.n = 0;
         cudaError_t pe = dispatch_fused(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream);
@@ -532,6 +575,15 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     if (!e) return fail(RSRL_EINVAL, "null engine");
     if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
     CU_TRY(cudaSetDevice(e->cfg.device));
+    if (e->f4) {
+        for (int64_t k = 0; k < k_steps; ++k) {
+            StepArgs a = make_args(e);
+            int rc = f4_step(e, a, false, e->N);
+            if (rc) return rc;
+            e->t += 1;
+        }
+        return RSRL_OK;
+    }
     if (e->tile) {
         if (e->world > 1) return fail(RSRL_EUNSUPPORTED, "TileCoding engines are single-GPU (shard envs with PER-GPU agents instead)");
         while (k_steps > 0) {
@@ -725,6 +777,7 @@ static int engine_eval(rsrl_engine* e, int mode, int64_t n, const double* states
     ea.out = mode == 1 ? dout.as<double>() : nullptr; ea.act_out = mode == 1 ? nullptr : dout.as<int32_t>();
     ea.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed); ea.draw = draw; ea.env_offset = e->cfg.env_offset; ea.counters = e->counters;
     if (e->tile) CU_TRY((e->cfg.dtype == RSRL_F32 ? launch_tile_eval_f32 : launch_tile_eval_f64)(e->cfg.domain, e->AW, ea, e->targs.tp, e->stream));
+    else if (e->f4) CU_TRY((e->cfg.dtype == RSRL_F32 ? launch_f4_eval_f32 : launch_f4_eval_f64)(e->cfg.domain, e->cfg.basis_order, ea, e->stream));
     else CU_TRY(dispatch_eval(e->key, ea, e->stream));
     e->launches += 1;
     if (mode == 1) CU_TRY(cudaMemcpyAsync(q_out, dout.p, (size_t)n * e->AW * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
@@ -771,7 +824,12 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
     a.n = n; a.t = draw; a.td = dtd.p;
     a.ext_from = dfrom.as<double>(); a.ext_to = dto.as<double>(); a.ext_actions = dact.as<int32_t>();
     a.ext_rewards = drew.as<double>(); a.ext_term = dterm.as<uint8_t>();
-    if (e->tile) {
+    if (e->f4) {
+        // the dW pass reads the caller's actions from the engine's action buffer
+        CU_TRY(cudaMemcpyAsync(e->actions, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        int rc = f4_step(e, a, true, n);
+        if (rc) return rc;
+    } else if (e->tile) {
         e->targs.barrier_base = e->tile_steps;
         int g2 = (int)((n + 127) / 128);
         if (g2 > e->pgrid) g2 = e->pgrid;
@@ -939,7 +997,8 @@ static int stateless_eval(const rsrl_config_t* cfg, int mode, int64_t n, const d
     memset(&ea, 0, sizeof ea);
     ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = dwr.p; ea.out = dout.as<double>();
     if (mode == 0 && cfg->basis == RSRL_TILE_CODING) CU_TRY(cudaMemset(dout.p, 0, out_elems * sizeof(double)));
-    cudaError_t ce = cfg->basis == RSRL_TILE_CODING
+    cudaError_t ce = is_f4(cfg) ? (cfg->dtype == RSRL_F32 ? launch_f4_eval_f32 : launch_f4_eval_f64)(cfg->domain, cfg->basis_order, ea, 0)
+                     : cfg->basis == RSRL_TILE_CODING
                          ? (cfg->dtype == RSRL_F32 ? launch_tile_eval_f32 : launch_tile_eval_f64)(cfg->domain, aw, ea, tile_params(cfg), 0)
                          : dispatch_eval(k, ea, 0);
     if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(cfg); }

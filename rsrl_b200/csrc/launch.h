@@ -42,6 +42,14 @@ typedef cudaError_t (*persist_launch_fn)(const BasisKey&, int weight_mode, const
 RSRL_DECL_INST(f32_d0) RSRL_DECL_INST(f32_d1) RSRL_DECL_INST(f32_d2)
 RSRL_DECL_INST(f64_d0) RSRL_DECL_INST(f64_d1) RSRL_DECL_INST(f64_d2)
 
+struct F4Args;
+cudaError_t launch_f4_env_f32(int domain, int order, bool ext, const StepArgs&, const F4Args&, int grid, int block, size_t smem, cudaStream_t);
+cudaError_t launch_f4_env_f64(int domain, int order, bool ext, const StepArgs&, const F4Args&, int grid, int block, size_t smem, cudaStream_t);
+cudaError_t launch_f4_dw_f32(int domain, int order, int64_t n, const double* from_states, const void* coef, const int32_t* actions, int n_seg, void* partials, cudaStream_t);
+cudaError_t launch_f4_dw_f64(int domain, int order, int64_t n, const double* from_states, const void* coef, const int32_t* actions, int n_seg, void* partials, cudaStream_t);
+cudaError_t launch_f4_eval_f32(int domain, int order, const EvalArgs&, cudaStream_t);
+cudaError_t launch_f4_eval_f64(int domain, int order, const EvalArgs&, cudaStream_t);
+
 struct TileArgs;
 struct TileParams;
 cudaError_t launch_tile_persist_f32(int domain, int aw, bool ext, const StepArgs&, int k, const TileArgs&, int grid, int block, size_t smem, cudaStream_t);

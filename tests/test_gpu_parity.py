@@ -528,3 +528,61 @@ def test_cfg3_full_size_properties(E):
     assert st["total_steps"] == 262144 * 120 and st["nonfinite"] == 0 and st["total_episodes"] > 0
     assert np.isfinite(W).all() and np.abs(W).max() > 0
     assert (np.abs(S[:, 0]) <= 2.4).all() and (np.abs(S[:, 2]) <= np.pi / 15).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# large Fourier bases on the 4-D domains (BASELINE config 4: Acrobot / ExpectedSARSA / Fourier(7), F = 4096)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("domain,order", [(AC, 7), (CP, 5)])
+@pytest.mark.parametrize("dtype,tol", [(abi.F64, 1e-13), (abi.F32, 2e-5)])
+def test_large_basis_project_and_evaluate(E, oracle, domain, order, dtype, tol):
+    cfg = abi.default_config(domain=domain, basis_order=order, dtype=dtype)
+    D, A = oracle.domain_dims(domain)
+    F = (order + 1) ** 4
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(order)
+    s = rng.uniform(lo, hi, size=(40, D))
+    s[0], s[1] = lo, hi
+    got, want = E.basis_project(cfg, s), oracle.project(cfg, s)
+    assert got.shape == (40, F) and np.abs(got - want).max() < tol * order
+    W = rng.normal(size=(F, A))
+    assert np.abs(E.lfa_evaluate(cfg, W, s) - oracle.evaluate(cfg, W, s)).max() < tol * 10 * np.sqrt(F)
+
+
+@pytest.mark.parametrize("domain,order,algo", [(AC, 7, abi.EXPECTED_SARSA), (CP, 5, abi.QLEARNING)])
+def test_large_basis_engine_free_run_f64(E, oracle, domain, order, algo):
+    cfg = abi.default_config(domain=domain, basis_order=order, algo=algo, policy=abi.EPSILON_GREEDY, epsilon=0.1, n_envs=70,
+                             dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.1] * 4, init_hi=[0.1] * 4,
+                             max_episode_steps=25, seed=17, gamma=0.99, lr=1e-4, alpha=1.0, record_td_error=1,
+                             update_scale=abi.SCALE_MEAN)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        for chunk in (1, 5, 34):
+            e.step(chunk)
+            o.step(chunk)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9, s_tol=1e-8)
+        assert o.stats()["total_episodes"] > 0
+        # trait-level entry points on the 4096-feature weights
+        s = e.states()
+        assert np.abs(e.evaluate(s) - oracle.evaluate(cfg, o.weights(), s)).max() < 1e-9
+        a = np.zeros(70, dtype=np.int32)
+        ns, r, term = oracle.domain_step(domain, s, a)
+        td_e, td_o = e.handle(s, a, r, ns, term, draw_idx=99), o.handle(s, a, r, ns, term, draw_idx=99)
+        assert np.abs(td_e - td_o).max() < 1e-9 and np.abs(e.weights() - o.weights()).max() < 1e-9
+
+
+def test_cfg4_shape_properties(E):
+    """Acrobot / ExpectedSARSA / Fourier(7) at a per-GPU shard of config 4: deterministic, finite, counted."""
+    cfg = abi.default_config(domain=AC, basis_order=7, algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1,
+                             n_envs=16384, dtype=abi.F32, init_mode=abi.INIT_UNIFORM, init_lo=[-0.1] * 4, init_hi=[0.1] * 4,
+                             max_episode_steps=500, seed=0, gamma=0.99, lr=1e-4, alpha=1.0, update_scale=abi.SCALE_MEAN)
+    outs = []
+    for _ in range(2):
+        with E.Engine(cfg) as e:
+            e.step(20)
+            e.sync()
+            outs.append((e.weights(), e.states(), e.stats()))
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+    assert outs[0][0].shape == (4096, 3) and np.isfinite(outs[0][0]).all() and np.abs(outs[0][0]).max() > 0
+    assert outs[0][2]["total_steps"] == 16384 * 20 and outs[0][2]["nonfinite"] == 0
