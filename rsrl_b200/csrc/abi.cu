@@ -119,10 +119,10 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     return table[k.dtype][k.domain](k, e, st);
 }
 
-static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
     static const persist_launch_fn table[2][3] = {{launch_persist_f32_d0, launch_persist_f32_d1, launch_persist_f32_d2},
                                                   {launch_persist_f64_d0, launch_persist_f64_d1, launch_persist_f64_d2}};
-    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, pe, cap, grid, block, smem, st);
+    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, pe, grid, block, smem, st);
 }
 
 static int unsupported(const rsrl_config_t* c) {
@@ -189,8 +189,8 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, nullptr, 0, 0};
-    size_t sync1_bytes = 0, sync2_bytes = 0;
+    SyncArgs sync = {nullptr, nullptr, 0, 0, 1, 1, 4, 0};
+    size_t sync1_bytes = 0, sync2_bytes = 0, stage3_bytes = 0;
     int pcap = 0;  // padded slot count of the CTA reduce buffers
     uint64_t t = 0;
     int64_t launches = 0;
@@ -273,15 +273,23 @@ static void choose_persistent(rsrl_engine* e) {
     if (block < 64) block = 64;
     if (block > 512) block = 512;
     if (block < rows) return;
+    // persistent.cuh shapes: lpr adjacent lanes own one row in the LL exchange; lpg adjacent lanes own a
+    // group of 4 rows in the CTA reduce, each lane summing one slot segment of seg_len slots.
     const int vn = (int)(16 / e->rsz);
-    int cap = (block + vn - 1) / vn * vn;
-    while ((cap / vn) % 2 == 0) cap += vn;  // cap / vn odd: conflict-free 16-byte row reads (persistent.cuh)
-    const int nseg = block / (int)rows > 0 ? block / (int)rows : 1;
-    const size_t vpl0 = e->cfg.dtype == RSRL_F32 ? 3 : 1;
-    const size_t nlv = (((size_t)e->FA + vpl0 - 1) / vpl0) * vpl0;
-    const size_t elems = (size_t)e->F * 4 + (size_t)(rows + (e->has_trace ? 1 : e->AW)) * cap + (size_t)nseg * e->FA + (2 * (size_t)kMaxFan + 1) * nlv;
+    int lpr = 8;
+    while ((int64_t)rows * lpr > block) lpr >>= 1;
+    const int64_t nrg = (rows + 3) / 4;
+    int lpg = 32;
+    while (nrg * lpg > block) lpg >>= 1;
+    int seg_len = ((block + lpg - 1) / lpg + vn - 1) / vn * vn;
+    if ((seg_len / vn) % 2 == 0) seg_len += vn;  // odd number of 16-byte groups: conflict-free segment reads
+    const int cap = lpg * seg_len;
+    const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;
+    const size_t elems = (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap + (size_t)nrg * 4 * ndc;
     const size_t bytes = elems * e->rsz;
     e->pcap = cap;
+    e->sync.lpr = lpr; e->sync.lpg = lpg; e->sync.seg_len = seg_len;
+    e->sync.debug_skip = getenv("RSRL_B200_DEBUG_SKIP") ? atoi(getenv("RSRL_B200_DEBUG_SKIP")) : 0;
     if (bytes > 220 * 1024) return;
     e->pgrid = grid; e->pblock = block; e->psmem = bytes;
     int gs = 1;
@@ -495,14 +503,16 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     }
     if (e->persistent && cfg->weight_mode == RSRL_SHARED) {
-        const size_t vpl = e->cfg.dtype == RSRL_F32 ? 3 : 1;  // values per 16-byte LL line
-        const size_t nl = ((size_t)e->FA + vpl - 1) / vpl;
+        const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;       // reduce rows
+        const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;                       // values per row
+        const size_t nl = rows * (e->cfg.dtype == RSRL_F32 ? 1 : ndc);             // 16-byte LL lines per partial
         e->sync1_bytes = (size_t)e->pgrid * nl * sizeof(uint4);
         e->sync2_bytes = (size_t)2 * e->sync.n_groups * nl * sizeof(uint4);
+        e->stage3_bytes = 2 * nl * sizeof(uint4);
         E_TRY(cudaMalloc(&e->sync.stage1, e->sync1_bytes));
         e->inbox_bytes = (size_t)2 * kMaxRanks * e->FA * (e->rsz / 4) * sizeof(uint2);
         E_TRY(cudaMalloc(&e->inbox, e->inbox_bytes));
-        E_TRY(cudaMalloc(&e->peer.stage3, 2 * nl * sizeof(uint4)));
+        E_TRY(cudaMalloc(&e->peer.stage3, e->stage3_bytes));
         E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
@@ -549,7 +559,7 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
         CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
         e->tile_steps = 0;
     }
-    if (e->peer.stage3) CU_TRY(cudaMemsetAsync(e->peer.stage3, 0, 2 * (((size_t)e->FA + (e->cfg.dtype == RSRL_F32 ? 3 : 1) - 1) / (e->cfg.dtype == RSRL_F32 ? 3 : 1)) * sizeof(uint4), st));
+    if (e->peer.stage3) CU_TRY(cudaMemsetAsync(e->peer.stage3, 0, e->stage3_bytes, st));
     e->t = 0;
     if (init_states) {
         CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -603,7 +613,7 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
         while (k_steps > 0) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
-            cudaError_t ce = dispatch_persist(e->key, e->pmode, a, k, e->sync, e->peer, e->pcap, e->pgrid, e->pblock, e->psmem, e->stream);
+            cudaError_t ce = dispatch_persist(e->key, e->pmode, a, k, e->sync, e->peer, e->pgrid, e->pblock, e->psmem, e->stream);
             if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
                 cudaGetLastError();
                 e->persistent = false;

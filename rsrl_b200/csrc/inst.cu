@@ -29,7 +29,7 @@ static cudaError_t launch_mode(int mode, bool ext, const StepArgs& a, int grid, 
 }
 
 template <int BASIS, int P, int AW, int MODE>
-static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
     auto kern = persistent_kernel<R, DOM, BASIS, P, AW, MODE>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -44,10 +44,10 @@ static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& s
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if ((long long)per_sm * sms < grid) return cudaErrorCooperativeLaunchTooLarge;
-        void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy, (void*)&cap, (void*)&pe};
+        void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy, (void*)&pe};
         return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st);
     }
-    kern<<<grid, block, smem, st>>>(a, k_steps, sy, cap, pe);
+    kern<<<grid, block, smem, st>>>(a, k_steps, sy, pe);
     return cudaGetLastError();
 }
 
@@ -90,12 +90,12 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
 }
 
 cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy,
-                                                   const PeerArgs& pe, int cap, int grid, int block, size_t smem, cudaStream_t st) {
+                                                   const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
     constexpr int A = Domain<DOM>::A;
 #define RSRL_PERSIST(B, P, AWV)                                                                                   \
-    (mode == RSRL_SHARED ? persist_one<B, P, AWV, RSRL_SHARED>(a, k_steps, sy, pe, cap, grid, block, smem, st)         \
-     : mode == RSRL_PER_ENV ? persist_one<B, P, AWV, RSRL_PER_ENV>(a, k_steps, sy, pe, cap, grid, block, smem, st)     \
-                            : persist_one<B, P, AWV, kModeSharedTrace>(a, k_steps, sy, pe, cap, grid, block, smem, st))
+    (mode == RSRL_SHARED ? persist_one<B, P, AWV, RSRL_SHARED>(a, k_steps, sy, pe, grid, block, smem, st)         \
+     : mode == RSRL_PER_ENV ? persist_one<B, P, AWV, RSRL_PER_ENV>(a, k_steps, sy, pe, grid, block, smem, st)     \
+                            : persist_one<B, P, AWV, kModeSharedTrace>(a, k_steps, sy, pe, grid, block, smem, st))
 #define X(B, P)                                   \
     if (k.basis == B && k.order == P) {           \
         if (k.aw == A) return RSRL_PERSIST(B, P, A); \

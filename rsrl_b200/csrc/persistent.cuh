@@ -4,23 +4,25 @@
 // tables of the current state live in registers for the whole launch (HBM traffic = one read + one
 // write of the state per launch).  SHARED weights need W_{t+1} = W_t + sum over ALL envs of the
 // step-t updates before anybody can take step t+1, so every step ends in a grid-wide, fixed-order
-// (bit-reproducible) reduction of F*A values:
+// (bit-reproducible) reduction of F*A values.  A feature row k (its A values) is owned, in every
+// CTA, by one group of `lpr` adjacent lanes:
 //
 //   CTA    : env threads write phi(s_t) (feature-major rows, lane = env slot: conflict-free) while
-//            they evaluate Q(s_t), and their scaled TD error per action column; (feature, segment)
-//            reducer threads then sum 4 slots per LDS.128 in slot order.
-//   hop 1  : every CTA publishes its partial as 16-byte LL lines {3 payload words, epoch}; the leader
-//            of each group of ~sqrt(G) CTAs collects its members' lines — one line per thread, so all
-//            L2 round trips overlap — and sums them in CTA order through shared memory.
-//   hop 2  : leaders publish the group partials (parity double-buffered); every CTA collects all of
-//            them (again one line per thread), sums in group order and updates its W copy.
-//            (Private per-destination mailboxes were tried: the 5 K strong stores per leader cost
-//            3 K cycles, more than the shared lines' polling contention.)
+//            they evaluate Q(s_t), and their scaled TD error per action column.  A reducer thread owns
+//            4 rows x one slot segment (one load of the TD errors feeds 4 rows: the phase is bound by
+//            the number of LDS.128, ~5 cycles each), a shuffle butterfly over the segment lanes
+//            finishes the CTA partial.
+//   hop 1  : lane 0 publishes the row as a 16-byte LL line {3 payload words, epoch}.  In the leader
+//            of each group of ~sqrt(G) CTAs, lane m of row k spins on member m's (and m + lpr's)
+//            line; a butterfly sums the members.
+//   hop 2  : the leader's lane 0 publishes the group partial (parity double-buffered); in every CTA
+//            lane g of row k spins on group g's line, a butterfly sums the groups, lane 0 updates W.
+//   hop 3  : (multi-GPU) CTA 0 writes its rows into every rank's inbox through NVLink peer pointers,
+//            sums the ranks' rows in the same lane pattern and re-publishes the total locally.
 //
-// No atomics, no fences, no grid.sync(): two LL hops per step with ~64 K 16-byte polls in flight
-// chip-wide.  (v2 polled 192 K 8-byte words with 12-16 dependent polls per thread and spent 4.7 us
-// per step in the exchange: profiles/r01_persistent_v1.md.)  Launched with
-// cudaLaunchCooperativeKernel so that all CTAs are co-resident (the spins need it).
+// No atomics, no fences, no grid.sync(), two barriers per step.  One LL hop costs ~700 cycles on a
+// B200 (tools/microbench/pingpong.cu); earlier versions and what they cost: profiles/r01_persistent_v1.md.
+// Launched with cudaLaunchCooperativeKernel so that all CTAs are co-resident (the spins need it).
 #pragma once
 #include "kernels.cuh"
 
@@ -28,20 +30,24 @@ namespace rsrl {
 
 constexpr int kMaxFan = 16;  // max CTAs per group and max groups (G <= 256)
 constexpr int kModeSharedTrace = 2;  // internal MODE: SHARED weights + per-env traces kept in shared memory
+constexpr int kMaxRanks = 8;
 
 struct SyncArgs {
-    uint4* stage1;  // [G][NL]             member partials
-    uint4* stage2;  // [2][n_groups][NL]   group partials (parity)
+    uint4* stage1;  // [G][ROWS * LPW]              CTA partial rows
+    uint4* stage2;  // [2][n_groups][ROWS * LPW]    group partial rows (parity)
     int group_size;
     int n_groups;
+    int lpr;        // LL lanes per row (power of two <= 8, ROWS * lpr <= blockDim)
+    int lpg;        // reducer lanes per group of 4 rows (power of two <= 32, ceil(ROWS / 4) * lpg <= blockDim)
+    int seg_len;    // slots per reducer lane (odd multiple of the 16-byte vector width); row stride cap = lpg * seg_len
+    int debug_skip; // development timing aid (RSRL_B200_DEBUG_SKIP): bit 0 skips the grid exchange, bit 1 the CTA reduce (wrong results)
 };
 
 // Cross-GPU exchange (one process per GPU): every rank owns an inbox of 8-byte LL words
 // {payload, epoch} that its peers write through NVLink (cudaIpc-mapped pointers).
-constexpr int kMaxRanks = 8;
 struct PeerArgs {
-    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][FA * WPV] as seen from this GPU
-    uint4* stage3;            // [2][NL] local broadcast of the all-GPU total (parity)
+    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][ROWS * NDC * WPV] as seen from this GPU
+    uint4* stage3;            // [2][ROWS * LPW] local broadcast of the all-GPU total (parity)
     int rank, world;
 };
 
@@ -53,7 +59,6 @@ __device__ __forceinline__ uint2 ld_ll8_sys(const uint2* p) {
 __device__ __forceinline__ void st_ll8_sys(uint2* p, uint32_t payload, uint32_t epoch) {
     asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
 }
-
 __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -63,40 +68,76 @@ __device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(epoch) : "memory");
 }
 
-// one 16-byte LL line carries VPL values + the epoch in the last word
-template <typename R> struct LL;
-template <> struct LL<float> {
-    static constexpr int VPL = 3;
+// A "row" carries NV <= 3 values.  fp32: one 16-byte LL line {v0, v1, v2, epoch}; fp64: one line per value.
+template <typename R, int NV> struct LLRow;
+template <int NV> struct LLRow<float, NV> {
+    static constexpr int LPW = 1;
     __device__ __forceinline__ static void publish(uint4* line, const float* v, uint32_t epoch) {
-        st_ll(line, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), epoch);
+        st_ll(line, __float_as_uint(v[0]), NV > 1 ? __float_as_uint(v[1]) : 0u, NV > 2 ? __float_as_uint(v[2]) : 0u, epoch);
     }
-    __device__ __forceinline__ static void unpack(const uint4& w, float* out) {
-        out[0] = __uint_as_float(w.x); out[1] = __uint_as_float(w.y); out[2] = __uint_as_float(w.z);
+    __device__ __forceinline__ static void load(const uint4* line, uint4* w) { w[0] = ld_ll(line); }
+    __device__ __forceinline__ static bool ready(const uint4* w, uint32_t epoch) { return w[0].w == epoch; }
+    __device__ __forceinline__ static void add(const uint4* w, float* acc) {
+        acc[0] += __uint_as_float(w[0].x);
+        if (NV > 1) acc[1] += __uint_as_float(w[0].y);
+        if (NV > 2) acc[2] += __uint_as_float(w[0].z);
     }
 };
-template <> struct LL<double> {
-    static constexpr int VPL = 1;
+template <int NV> struct LLRow<double, NV> {
+    static constexpr int LPW = NV;
     __device__ __forceinline__ static void publish(uint4* line, const double* v, uint32_t epoch) {
-        const unsigned long long u = (unsigned long long)__double_as_longlong(v[0]);
-        st_ll(line, (uint32_t)u, (uint32_t)(u >> 32), 0u, epoch);
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            const unsigned long long u = (unsigned long long)__double_as_longlong(v[c]);
+            st_ll(line + c, (uint32_t)u, (uint32_t)(u >> 32), 0u, epoch);
+        }
     }
-    __device__ __forceinline__ static void unpack(const uint4& w, double* out) {
-        out[0] = __longlong_as_double((long long)(((unsigned long long)w.y << 32) | w.x));
+    __device__ __forceinline__ static void load(const uint4* line, uint4* w) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) w[c] = ld_ll(line + c);
+    }
+    __device__ __forceinline__ static bool ready(const uint4* w, uint32_t epoch) {
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) ok &= w[c].w == epoch;
+        return ok;
+    }
+    __device__ __forceinline__ static void add(const uint4* w, double* acc) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) acc[c] += __longlong_as_double((long long)(((unsigned long long)w[c].y << 32) | w[c].x));
     }
 };
 
-// sum of rows[m * stride], m = 0..cnt-1 ascending; loads issued four at a time (latency overlap), fixed association
-template <typename R>
-__device__ __forceinline__ R sum_rows(const R* rows, int stride, int cnt) {
-    R acc = (R)0;
-    int m = 0;
-    for (; m + 4 <= cnt; m += 4) {
-        const R v0 = rows[(size_t)(m + 0) * stride], v1 = rows[(size_t)(m + 1) * stride];
-        const R v2 = rows[(size_t)(m + 2) * stride], v3 = rows[(size_t)(m + 3) * stride];
-        acc = (((acc + v0) + v1) + v2) + v3;
+// acc = sum of the rows published by producers m = first, first + step, ... (< cnt) at base + m * stride;
+// two producers are polled at a time so that their L2 round trips overlap.
+template <typename R, int NV>
+__device__ __forceinline__ void ll_gather(const uint4* base, size_t stride, int first, int step, int cnt, uint32_t epoch, bool valid, R* acc) {
+    using LR = LLRow<R, NV>;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] = (R)0;
+    if (!valid) return;
+    for (int m = first; m < cnt; m += 2 * step) {
+        const int m2 = m + step;
+        const bool two = m2 < cnt;
+        uint4 w0[LR::LPW], w1[LR::LPW];
+        LR::load(base + (size_t)m * stride, w0);
+        if (two) LR::load(base + (size_t)m2 * stride, w1);
+        while (!LR::ready(w0, epoch)) LR::load(base + (size_t)m * stride, w0);
+        LR::add(w0, acc);
+        if (two) {
+            while (!LR::ready(w1, epoch)) LR::load(base + (size_t)m2 * stride, w1);
+            LR::add(w1, acc);
+        }
     }
-    for (; m < cnt; ++m) acc += rows[(size_t)m * stride];
-    return acc;
+}
+
+// fixed-order butterfly over the lpr adjacent lanes that own one row (executed by whole warps)
+template <typename R, int NV>
+__device__ __forceinline__ void row_butterfly(R* v, int lpr) {
+    for (int off = 1; off < lpr; off <<= 1) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], off);
+    }
 }
 
 template <typename R> struct Vec16;  // 16-byte shared-memory vector of R
@@ -106,11 +147,10 @@ __device__ __forceinline__ float vget(const float4& v, int i) { return i == 0 ? 
 __device__ __forceinline__ double vget(const double2& v, int i) { return i == 0 ? v.x : v.y; }
 
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE>
-__global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const int cap, const PeerArgs pe) {
+__global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     using O = RealOps<R>;
-    using L = LL<R>;
     using V = Vec16<R>;
     typedef typename V::type vec_t;
     constexpr int D = Dom::D, F = GB::F, FA = F * AW;
@@ -118,10 +158,12 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     constexpr bool SHAREDW = MODE != RSRL_PER_ENV;          // one replicated W, dW reduced over the grid
     constexpr bool TRACE = MODE == kModeSharedTrace;        // eligibility traces resident in shared memory
     constexpr int ROWS = TRACE ? FA : F;                    // rows of the reduce buffer: z (F*A) or phi(s_t) (F)
-    constexpr int NDC = TRACE ? 1 : AW;                     // rows of scaled TD errors
+    constexpr int NDC = TRACE ? 1 : AW;                     // values per row = rows of scaled TD errors
     constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
     constexpr int FApad = F * WS;
-    constexpr int NL = (FA + L::VPL - 1) / L::VPL;  // LL lines per partial
+    using LR = LLRow<R, NDC>;
+    constexpr int LPW = LR::LPW;     // LL lines per row
+    constexpr int WPV = sizeof(R) / 4;
 
     const int tid = threadIdx.x, BLOCK = blockDim.x, G = gridDim.x, b = blockIdx.x;
     const int64_t N = a.n;
@@ -130,24 +172,22 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const int64_t end = base + per_cta < N ? base + per_cta : N;
     const int n_chunks = (int)((per_cta + BLOCK - 1) / BLOCK);
     const bool resident = n_chunks == 1;  // one env per thread: state stays in registers across steps
+    const int lpr = sy.lpr, lpg = sy.lpg, seg_len = sy.seg_len, cap = lpg * seg_len;
+    constexpr int RPT = 4;                      // rows per reducer thread: one dcs load feeds RPT rows
+    constexpr int ROWSP = (ROWS + RPT - 1) / RPT * RPT;
 
-    // shared memory (SHARED mode): cap = padded slot count, a multiple of V::N with cap / V::N odd, so
-    // that the 8 lanes of a quarter warp reading red[k][slot..] at consecutive k hit 8 distinct 16-byte
-    // bank groups.  Rows of slots >= BLOCK are zero and stay zero.
+    // shared memory (SHARED mode).  Row stride cap = lpr * seg_len with seg_len / V::N odd: the lpr lanes
+    // of a row read 16-byte groups seg * seg_len + slot that fall into distinct bank groups.  Slots
+    // >= BLOCK are zero and stay zero.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* Wsm = reinterpret_cast<R*>(smem_raw);  // [FApad]
-    R* red = Wsm + FApad;                     // [ROWS][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
-    R* dcs = red + (size_t)ROWS * cap;        // [NDC][cap]  scaled TD error in the action's row, 0 elsewhere
-    const int nseg = BLOCK / ROWS > 0 ? BLOCK / ROWS : 1;
-    const int seg_len = (((cap + nseg - 1) / nseg) + V::N - 1) / V::N * V::N;
-    R* segpart = dcs + (size_t)NDC * cap;     // [nseg][FA]
-    constexpr int NLV = NL * L::VPL;          // values per partial, padded to whole LL lines
-    R* stgA = segpart + (size_t)nseg * FA;    // [kMaxFan + 1][NLV] hop-1 staging (leader) + the group partial
-    R* stgB = stgA + (size_t)(kMaxFan + 1) * NLV;  // [kMaxFan][NLV] own partial, then hop-2 staging
+    R* red = Wsm + FApad;                     // [ROWSP][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
+    R* dcs = red + (size_t)ROWSP * cap;       // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
+    R* part = dcs + (size_t)NDC * cap;        // [ROWSP][NDC] this CTA's dW rows (reducers -> LL lanes)
 
     if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
-        for (int j = tid; j < (ROWS + NDC) * cap; j += BLOCK) red[j] = (R)0;
+        for (int j = tid; j < (ROWSP + NDC) * cap; j += BLOCK) red[j] = (R)0;
         __syncthreads();
     }
     const R* Wg = static_cast<const R*>(a.W);
@@ -169,18 +209,27 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     typename GB::Tab tab_s, tab_n;
     bool have_tab = false;  // tab_s holds the tables of s (carried from the previous step's s')
 
-    // reducer role: (seg, k) sums phi[k][slot] * dcs[:][slot] over its slots
-    const bool reducer = SHAREDW && tid < nseg * ROWS;
-    const int rk = tid % ROWS, rseg = tid / ROWS;
+    // reducers: lanes [rg * lpg, (rg + 1) * lpg) own rows 4 rg .. 4 rg + 3; lane `rseg` sums slot segment rseg
+    const int rg = tid / lpg, rseg = tid % lpg;
+    const bool reducer = SHAREDW && rg < ROWSP / RPT;
+    const bool warp_red = SHAREDW && (tid & ~31) < (ROWSP / RPT) * lpg;  // warp-uniform
+    // LL row ownership: lanes [row * lpr, (row + 1) * lpr) own row `row` in the grid exchange
+    const int row = tid / lpr, rl = tid % lpr;
+    const bool row_valid = SHAREDW && row < ROWS;
+    const bool warp_rows = SHAREDW && (tid & ~31) < ROWS * lpr;  // warp-uniform: this warp owns at least one row
+    const int grp = b / sy.group_size;
+    const bool leader = b % sy.group_size == 0;
 
     const bool prof = a.phase_prof != nullptr && tid == 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0, c2 = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0;
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
         if (prof) c0 = clock64();
-        R racc[2][NDC];
+        R racc[RPT][NDC];
 #pragma unroll
-        for (int c = 0; c < NDC; ++c) racc[0][c] = racc[1][c] = (R)0;
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+            for (int c = 0; c < NDC; ++c) racc[r][c] = (R)0;
 
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             if (!resident) {
@@ -282,32 +331,26 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 // (a slot idle in this chunk keeps a stale but finite row; its dcs entries are 0)
                 __syncthreads();
                 if (prof) { c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
-                if (reducer) {
+                if (reducer && !(sy.debug_skip & 2)) {
                     const int s0 = rseg * seg_len;
-                    const int s1 = s0 + seg_len < cap ? s0 + seg_len : cap;
-                    const R* prow = red + (size_t)rk * cap;
-                    // two interleaved accumulator sets (even / odd 16-byte groups) hide the LDS + FMA latency
-                    for (int slot = s0; slot < s1; slot += 2 * V::N) {
-                        const bool two = slot + V::N < s1;
-                        const vec_t pv0 = *reinterpret_cast<const vec_t*>(prow + slot);
-                        const vec_t pv1 = two ? *reinterpret_cast<const vec_t*>(prow + slot + V::N) : pv0;
-                        vec_t dv0[NDC], dv1[NDC];
+                    const R* prow = red + (size_t)(rg * RPT) * cap + s0;
+                    const R* drow = dcs + s0;
+                    for (int slot = 0; slot < seg_len; slot += V::N) {
+                        vec_t dv[NDC];
 #pragma unroll
-                        for (int c = 0; c < NDC; ++c) {
-                            dv0[c] = *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot);
-                            dv1[c] = two ? *reinterpret_cast<const vec_t*>(dcs + (size_t)c * cap + slot + V::N) : dv0[c];
-                        }
+                        for (int c = 0; c < NDC; ++c) dv[c] = *reinterpret_cast<const vec_t*>(drow + (size_t)c * cap + slot);
 #pragma unroll
-                        for (int u = 0; u < V::N; ++u) {
+                        for (int r = 0; r < RPT; ++r) {
+                            const vec_t pv = *reinterpret_cast<const vec_t*>(prow + (size_t)r * cap + slot);
 #pragma unroll
-                            for (int c = 0; c < NDC; ++c) {
-                                racc[0][c] = O::fma(vget(pv0, u), vget(dv0[c], u), racc[0][c]);
-                                if (two) racc[1][c] = O::fma(vget(pv1, u), vget(dv1[c], u), racc[1][c]);
+                            for (int u = 0; u < V::N; ++u) {
+#pragma unroll
+                                for (int c = 0; c < NDC; ++c) racc[r][c] = O::fma(vget(pv, u), vget(dv[c], u), racc[r][c]);
                             }
                         }
                     }
                 }
-                __syncthreads();
+                if (n_chunks > 1 || TRACE) __syncthreads();  // rows are rewritten by the next chunk / cleared below
                 if (TRACE && active && o.terminated) {  // trace.reset() (sarsa_lambda.rs:78, q_lambda.rs:81, td_lambda.rs:61)
                     for (int j = 0; j < FA; ++j) red[(size_t)j * cap + tid] = (R)0;
                 }
@@ -315,107 +358,102 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         }
 
         if (SHAREDW) {
-            if (reducer) {
+            // CTA partial: butterfly over the lpg lanes of each row group, lane 0 hands the rows to the LL lanes
+            if (warp_red) {
+                for (int off = 1; off < lpg; off <<= 1) {
 #pragma unroll
-                for (int c = 0; c < NDC; ++c) segpart[rseg * FA + (TRACE ? rk : rk * AW + c)] = racc[0][c] + racc[1][c];
+                    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                        for (int c = 0; c < NDC; ++c) racc[r][c] += __shfl_xor_sync(0xffffffffu, racc[r][c], off);
+                }
+                if (reducer && rseg == 0) {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                        for (int c = 0; c < NDC; ++c) part[(rg * RPT + r) * NDC + c] = racc[r][c];
+                }
             }
             __syncthreads();
-            if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
-            const uint32_t epoch = (uint32_t)(t + 1);
-            const int par = (int)(t & 1);
-            const int grp = b / sy.group_size;
-            // this CTA's partial: segment-order sum, loads issued four at a time so their latencies overlap
-            for (int idx = tid; idx < NLV; idx += BLOCK) {
-                R m = (R)0;
-                if (idx < FA) {
-                    int sg = 0;
-                    for (; sg + 4 <= nseg; sg += 4) {
-                        const R v0 = segpart[(sg + 0) * FA + idx], v1 = segpart[(sg + 1) * FA + idx];
-                        const R v2 = segpart[(sg + 2) * FA + idx], v3 = segpart[(sg + 3) * FA + idx];
-                        m = (((m + v0) + v1) + v2) + v3;
+            if (warp_rows) {
+                const uint32_t epoch = (uint32_t)(t + 1);
+                const int par = (int)(t & 1);
+                R dW[NDC];
+#pragma unroll
+                for (int c = 0; c < NDC; ++c) dW[c] = row_valid ? part[row * NDC + c] : (R)0;
+                if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
+                if (G > 1 && !(sy.debug_skip & 1)) {
+                    const size_t rstride = (size_t)ROWS * LPW;  // lines between two producers
+                    if (row_valid && rl == 0) LR::publish(sy.stage1 + (size_t)b * rstride + (size_t)row * LPW, dW, epoch);
+                    if (leader) {  // hop 1: lane m gathers member m (and m + lpr, ...) of this row
+                        const int first = grp * sy.group_size;
+                        const int cnt = G - first < sy.group_size ? G - first : sy.group_size;
+                        R gsum[NDC];
+                        ll_gather<R, NDC>(sy.stage1 + (size_t)first * rstride + (size_t)row * LPW, rstride, rl, lpr, cnt, epoch, row_valid, gsum);
+                        __syncwarp();
+                        row_butterfly<R, NDC>(gsum, lpr);
+                        if (row_valid && rl == 0) LR::publish(sy.stage2 + ((size_t)par * sy.n_groups + grp) * rstride + (size_t)row * LPW, gsum, epoch);
                     }
-                    for (; sg < nseg; ++sg) m += segpart[sg * FA + idx];
+                    // hop 2: lane g gathers group g (and g + lpr, ...) of this row
+                    ll_gather<R, NDC>(sy.stage2 + (size_t)par * sy.n_groups * rstride + (size_t)row * LPW, rstride, rl, lpr, sy.n_groups, epoch, row_valid, dW);
+                    __syncwarp();
+                    row_butterfly<R, NDC>(dW, lpr);
                 }
-                stgB[idx] = m;
+                if (pe.world > 1) {
+                    // hop 3 (NVLink): CTA 0 of every GPU writes its rows into every rank's inbox, gathers the world's
+                    // rows from its own inbox (lane r <-> rank r, butterfly => the same rank-pairing order on every
+                    // GPU => bit-identical replicas) and re-publishes the total for the local CTAs.
+                    constexpr int RW = NDC * WPV;  // 32-bit payload words per row
+                    if (b == 0) {
+                        if (row_valid && rl == 0) {
+                            uint32_t w[RW];
+#pragma unroll
+                            for (int c = 0; c < NDC; ++c) {
+                                if (WPV == 1) w[c] = __float_as_uint((float)dW[c]);
+                                else { const unsigned long long u = (unsigned long long)__double_as_longlong((double)dW[c]); w[c * WPV] = (uint32_t)u; w[c * WPV + WPV - 1] = (uint32_t)(u >> 32); }
+                            }
+                            for (int r = 0; r < pe.world; ++r) {
+                                uint2* dst = pe.inbox[r] + (((size_t)par * pe.world + pe.rank) * ROWS + row) * RW;
+#pragma unroll
+                                for (int q = 0; q < RW; ++q) st_ll8_sys(dst + q, w[q], epoch);
+                            }
+                        }
+                        R tot[NDC];
+#pragma unroll
+                        for (int c = 0; c < NDC; ++c) tot[c] = (R)0;
+                        if (row_valid) {
+                            for (int r = rl; r < pe.world; r += lpr) {
+                                const uint2* src = pe.inbox[pe.rank] + (((size_t)par * pe.world + r) * ROWS + row) * RW;
+                                uint32_t w[RW];
+#pragma unroll
+                                for (int q = 0; q < RW; ++q) {
+                                    uint2 v = ld_ll8_sys(src + q);
+                                    while (v.y != epoch) v = ld_ll8_sys(src + q);
+                                    w[q] = v.x;
+                                }
+#pragma unroll
+                                for (int c = 0; c < NDC; ++c) {
+                                    if (WPV == 1) tot[c] += (R)__uint_as_float(w[c]);
+                                    else tot[c] += (R)__longlong_as_double((long long)(((unsigned long long)w[c * WPV + WPV - 1] << 32) | w[c * WPV]));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        row_butterfly<R, NDC>(tot, lpr);
+#pragma unroll
+                        for (int c = 0; c < NDC; ++c) dW[c] = tot[c];
+                        if (G > 1 && row_valid && rl == 0) LR::publish(pe.stage3 + ((size_t)par * ROWS + row) * LPW, dW, epoch);
+                    } else {
+                        ll_gather<R, NDC>(pe.stage3 + ((size_t)par * ROWS + row) * LPW, 0, 0, 1, (row_valid && rl == 0) ? 1 : 0, epoch, row_valid, dW);
+                    }
+                }
+                if (row_valid && rl == 0) {
+#pragma unroll
+                    for (int c = 0; c < NDC; ++c) {
+                        const int idx = TRACE ? row : row * AW + c;  // flat F x A index
+                        Wsm[(idx / AW) * WS + idx % AW] += dW[c];
+                    }
+                }
             }
-            __syncthreads();
-            if (G > 1) {
-                // hop 1: publish the partial as LL lines
-                for (int j = tid; j < NL; j += BLOCK) L::publish(sy.stage1 + (size_t)b * NL + j, stgB + j * L::VPL, epoch);
-                if (prof) { c2 = clock64(); pc[5] += c2 - c0; }
-                if (b % sy.group_size == 0) {  // group leader (CTA-uniform branch)
-                    const int first = grp * sy.group_size;
-                    const int cnt = G - first < sy.group_size ? G - first : sy.group_size;
-                    for (int p = tid; p < cnt * NL; p += BLOCK) {  // every thread polls one line: all round trips overlap
-                        const int m = p / NL, j = p % NL;
-                        const uint4* line = sy.stage1 + (size_t)(first + m) * NL + j;
-                        uint4 w = ld_ll(line);
-                        while (w.w != epoch) w = ld_ll(line);
-                        L::unpack(w, stgA + (size_t)m * NLV + j * L::VPL);
-                    }
-                    __syncthreads();
-                    if (prof) { c1 = clock64(); pc[6] += c1 - c2; c2 = c1; }
-                    for (int idx = tid; idx < NLV; idx += BLOCK) stgA[(size_t)kMaxFan * NLV + idx] = sum_rows<R>(stgA + idx, NLV, cnt);  // CTA order
-                    __syncthreads();
-                    for (int j = tid; j < NL; j += BLOCK)
-                        L::publish(sy.stage2 + ((size_t)par * sy.n_groups + grp) * NL + j, stgA + (size_t)kMaxFan * NLV + j * L::VPL, epoch);
-                    if (prof) { c1 = clock64(); pc[7] += c1 - c2; c2 = c1; }
-                }
-                // hop 2: every CTA collects all group partials (parity double-buffered) and sums in group order
-                __syncthreads();  // everybody is done reading stgB (the hop-1 publish)
-                for (int p = tid; p < sy.n_groups * NL; p += BLOCK) {
-                    const int g2 = p / NL, j = p % NL;
-                    const uint4* line = sy.stage2 + ((size_t)par * sy.n_groups + g2) * NL + j;
-                    uint4 w = ld_ll(line);
-                    while (w.w != epoch) w = ld_ll(line);
-                    L::unpack(w, stgB + (size_t)g2 * NLV + j * L::VPL);
-                }
-                __syncthreads();
-                for (int idx = tid; idx < NLV; idx += BLOCK) stgA[idx] = idx < FA ? sum_rows<R>(stgB + idx, NLV, sy.n_groups) : (R)0;
-            } else {
-                for (int idx = tid; idx < NLV; idx += BLOCK) stgA[idx] = stgB[idx];
-            }
-            __syncthreads();  // stgA[0..NLV) = this GPU's dW
-            if (pe.world > 1) {
-                // hop 3 (NVLink): CTA 0 of every GPU writes its dW into every rank's inbox, collects the
-                // world's partials from its own inbox, sums them in rank order (=> bit-identical replicas)
-                // and broadcasts the total to the local CTAs.  The transfer is part of this kernel.
-                constexpr int WPV = sizeof(R) / 4;
-                constexpr int FAW = FA * WPV;
-                uint32_t* words = reinterpret_cast<uint32_t*>(stgB);  // [world][FAW]
-                if (b == 0) {
-                    const uint32_t* mine_w = reinterpret_cast<const uint32_t*>(stgA);
-                    for (int p = tid; p < pe.world * FAW; p += BLOCK) {
-                        const int r = p / FAW, w = p % FAW;
-                        st_ll8_sys(pe.inbox[r] + ((size_t)par * pe.world + pe.rank) * FAW + w, mine_w[w], epoch);
-                    }
-                    for (int p = tid; p < pe.world * FAW; p += BLOCK) {
-                        const int r = p / FAW, w = p % FAW;
-                        const uint2* slot = pe.inbox[pe.rank] + ((size_t)par * pe.world + r) * FAW + w;
-                        uint2 v = ld_ll8_sys(slot);
-                        while (v.y != epoch) v = ld_ll8_sys(slot);
-                        words[r * FAW + w] = v.x;
-                    }
-                    __syncthreads();
-                    for (int idx = tid; idx < FA; idx += BLOCK) {
-                        R tot = (R)0;
-                        for (int r = 0; r < pe.world; ++r) tot += reinterpret_cast<const R*>(words + (size_t)r * FAW)[idx];  // rank order
-                        stgA[idx] = tot;
-                    }
-                    __syncthreads();
-                    if (G > 1)
-                        for (int j = tid; j < NL; j += BLOCK) L::publish(pe.stage3 + (size_t)par * NL + j, stgA + j * L::VPL, epoch);
-                } else {
-                    for (int j = tid; j < NL; j += BLOCK) {
-                        const uint4* line = pe.stage3 + (size_t)par * NL + j;
-                        uint4 w = ld_ll(line);
-                        while (w.w != epoch) w = ld_ll(line);
-                        L::unpack(w, stgA + j * L::VPL);
-                    }
-                }
-                __syncthreads();
-            }
-            for (int idx = tid; idx < FA; idx += BLOCK) Wsm[(idx / AW) * WS + idx % AW] += stgA[idx];
             if (prof) { c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
             __syncthreads();
             if (prof) { c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }

@@ -31,3 +31,9 @@ if __name__ == "__main__":
     run("cfg5 sarsa(lambda) N=32768 (smem traces)", n_envs=32768, policy=abi.EPSILON_GREEDY, epsilon=0.2, algo=abi.SARSA_LAMBDA,
         alpha=0.01, gamma=0.99, k=1000)
     run("cfg5 td(lambda) N=32768 (smem traces)", n_envs=32768, policy=abi.RANDOM, algo=abi.TD_LAMBDA, gamma=0.99, k=1000)
+    run("cfg3 cartpole sarsa tile N=262144", n_envs=262144, domain=abi.CART_POLE, basis=abi.TILE_CODING, algo=abi.SARSA,
+        policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=0.1 / 8, init_lo=[-0.05] * 4, init_hi=[0.05] * 4,
+        max_episode_steps=500, k=300)
+    run("cfg4 acrobot esarsa fourier7 N=131072", n_envs=131072, domain=abi.ACROBOT, basis_order=7, algo=abi.EXPECTED_SARSA,
+        policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=1e-4, alpha=1.0, init_lo=[-0.1] * 4, init_hi=[0.1] * 4,
+        max_episode_steps=500, k=20)
