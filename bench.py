@@ -46,7 +46,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -107,7 +107,7 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as O
     O.build()
     threads = os.cpu_count() or 1
-    envs_per_thread, k = 64, 400   # sample: threads*64 envs x 400 steps per bench step (~1-2 s of CPU work)
+    envs_per_thread, k = 64, 2000   # sample: threads*64 envs x 2000 steps per bench step (~0.4 s of CPU work each)
     cfg = make_cfg(abi, abi.F64, envs_per_thread, mode=abi.PER_ENV)
     for _ in range(args.warmup):
         O.baseline_run(cfg, threads, envs_per_thread, 50)
@@ -258,9 +258,9 @@ def main():
         threads = os.cpu_count() or 1
         ccfg = make_cfg(abi, abi.F64, 64, mode=abi.PER_ENV)
         O.baseline_run(ccfg, threads, 64, 100)
-        secs, n = O.baseline_run(ccfg, threads, 64, 4000)
+        secs, n = O.baseline_run(ccfg, threads, 64, 60000)   # ~10-15 s of CPU work on all host cores
         out["cpu_baseline"] = {"value": n / secs, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{threads} threads x 64 independent single-env reference-shaped agents x 4000 steps ({secs:.1f} s)"}
+                               "sample": f"{threads} threads x 64 independent single-env reference-shaped agents x 60000 steps ({secs:.1f} s)"}
     if rank == 0:
         print(json.dumps(out))
     eng.close()

@@ -586,3 +586,32 @@ def test_cfg4_shape_properties(E):
     assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
     assert outs[0][0].shape == (4096, 3) and np.isfinite(outs[0][0]).all() and np.abs(outs[0][0]).max() > 0
     assert outs[0][2]["total_steps"] == 16384 * 20 and outs[0][2]["nonfinite"] == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# C++ host-side mirror of the reference's trait surface (include/rsrl_b200.hpp): examples/q_learning.cpp is
+# rsrl/examples/q_learning.rs line by line; its episode lengths must equal the oracle's.
+# ---------------------------------------------------------------------------------------------
+def test_cpp_mirror_example_matches_oracle(E, oracle):
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "q_learning")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build_examples()
+    out = subprocess.run([exe, "3", "2500"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    lengths = [int(m) for m in re.findall(r"Batch \d+: (\d+) steps", out.stdout)]
+    assert len(lengths) == 3
+    cfg = abi.default_config(dtype=abi.F64, max_episode_steps=2500)   # exactly examples/q_learning.rs + the cap
+    o = oracle.Engine(cfg)
+    o.step(sum(lengths))
+    n_ep, last_len, h = o.env_stats()
+    want = 0
+    for n in lengths:
+        want = (want * 1000003 + n) % (1 << 64)
+    assert n_ep[0] == 3 and int(h[0]) == want and last_len[0] == lengths[-1]
+    norm = float(re.search(r"\|W\|\^2 = (\S+)", out.stdout).group(1))
+    assert abs(norm - float((o.weights() ** 2).sum())) < 1e-12 * max(1.0, norm)
