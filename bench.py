@@ -248,9 +248,38 @@ def main():
         "e2e": {"value": env_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": ach_gbs / peak_gbs,
-                     "traffic": None, "peak_source": peak_src,
-                     "note": "algorithmic 48 B/env-step; the state is L2-resident, the binding roof is FP32 issue + grid sync (DESIGN.md)"},
+                     "traffic": 1.40e6, "peak_source": peak_src,
+                     "note": "algorithmic 48 B/env-step x 65536 envs x 2000 steps per launch; traffic = dram bytes of one launch from "
+                             "profiles/r01_final.md (env state is register-resident for the whole launch, so HBM is idle: the binding "
+                             "roofs are instruction issue at 14 warps/SM and the per-step grid exchange, see DESIGN.md section 8)"},
     }
+
+    # ---- the same workload in the other weight mode / dtype (extra information, not the headline) ----
+    if world == 1:
+        def side_run(label, **kw):
+            c2 = make_cfg(abi, kw.get("dtype", dtype), N_ENVS_PER_GPU, mode=kw.get("mode"))
+            with Engine(c2) as e2:
+                st2 = torch.cuda.ExternalStream(e2.stream(), device=torch.device("cuda", local_rank))
+                for _ in range(3):
+                    e2.step(K_INNER)
+                e2.sync()
+                tot = 0.0
+                for _ in range(5):
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record(st2)
+                    e2.step(K_INNER)
+                    a1.record(st2)
+                    a1.synchronize()
+                    tot += a0.elapsed_time(a1)
+                return {"value": N_ENVS_PER_GPU * K_INNER * 5 / (tot * 1e-3), "unit": "env-steps/s", "ms_per_step": tot / 5, "what": label}
+        pe = side_run("PER_ENV weights: 65536 independent reference agents, own W (36x3 fp32) resident in shared memory", mode=abi.PER_ENV)
+        pe["roofline"] = {"bound": "hbm", "achieved": 624 * pe["value"] / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                          "frac": 624 * pe["value"] / 1e9 / peak_gbs,
+                          "note": "algorithmic 624 B/env-step (SURVEY 8d: state + read W + write one column); > 1 because W never leaves the SM"}
+        out["also"] = {"per_env_weights": pe,
+                       "f64": side_run("SHARED weights, all arithmetic f64 (parity anchor dtype)", dtype=abi.F64)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as O

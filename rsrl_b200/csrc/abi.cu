@@ -189,7 +189,7 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, nullptr, 0, 0, 1, 1, 4, 0};
+    SyncArgs sync = {nullptr, nullptr, 0, 0, 1, 1, 4, 0, 0};
     size_t sync1_bytes = 0, sync2_bytes = 0, stage3_bytes = 0;
     int pcap = 0;  // padded slot count of the CTA reduce buffers
     uint64_t t = 0;
@@ -255,7 +255,10 @@ static void choose_persistent(rsrl_engine* e) {
     if (e->cfg.weight_mode == RSRL_PER_ENV) {
         e->pblock = 128;
         e->pgrid = (int)((e->N + e->pblock - 1) / e->pblock);
-        e->psmem = 0;
+        // every env's own W in shared memory (F*A x 128 columns) when at least two CTAs still fit on an SM
+        const size_t wbytes = (size_t)e->FA * e->pblock * e->rsz;
+        e->sync.pe_smem = wbytes <= 110 * 1024 ? 1 : 0;
+        e->psmem = e->sync.pe_smem ? wbytes : 0;
         e->persistent = true;
         return;
     }

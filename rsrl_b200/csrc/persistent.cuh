@@ -40,6 +40,7 @@ struct SyncArgs {
     int lpr;        // LL lanes per row (power of two <= 8, ROWS * lpr <= blockDim)
     int lpg;        // reducer lanes per group of 4 rows (power of two <= 32, ceil(ROWS / 4) * lpg <= blockDim)
     int seg_len;    // slots per reducer lane (odd multiple of the 16-byte vector width); row stride cap = lpg * seg_len
+    int pe_smem;    // PER_ENV: keep every env's own W (F*A values, column `tid`) in shared memory for the whole launch
     int debug_skip; // development timing aid (RSRL_B200_DEBUG_SKIP): bit 0 skips the grid exchange, bit 1 the CTA reduce (wrong results)
 };
 
@@ -191,6 +192,8 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         __syncthreads();
     }
     const R* Wg = static_cast<const R*>(a.W);
+    R* Wpe = reinterpret_cast<R*>(smem_raw);  // PER_ENV + pe_smem: [FA][BLOCK], column tid = this env's weights
+    const bool pe_smem = !SHAREDW && sy.pe_smem != 0;
 
     // resident env state
     double s[D];
@@ -201,6 +204,9 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
         for (int d = 0; d < D; ++d) s[d] = a.states[i * D + d];
         ep = a.ep_steps[i];
+    }
+    if (pe_smem && active) {  // this env's weights: HBM -> shared memory once per launch (read again only at the end)
+        for (int j = 0; j < FA; ++j) Wpe[(size_t)j * BLOCK + tid] = Wg[(int64_t)j * N + i];
     }
     if (TRACE && active) {  // this env's trace column: HBM -> shared memory once per launch
         const R* Z = static_cast<const R*>(a.z);
@@ -258,6 +264,9 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
                             for (int c = 0; c < AW; ++c) w[c] = c < 2 ? vget(v0, c) : vget(v1, c - 2);
                         }
+                    } else if (pe_smem) {
+#pragma unroll
+                        for (int c = 0; c < AW; ++c) w[c] = Wpe[(size_t)(k * AW + c) * BLOCK + tid];
                     } else {
 #pragma unroll
                         for (int c = 0; c < AW; ++c) w[c] = Wg[(int64_t)(k * AW + c) * N + i];
@@ -291,8 +300,14 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 if (MODE == RSRL_PER_ENV) {
                     R* Wm = static_cast<R*>(a.W);
                     GB::for_each(tab_s, [&](int k, R phi) {
-                        const int64_t idx = (int64_t)(k * AW + (TDPRED ? 0 : o.act)) * N + i;
-                        Wm[idx] = O::mul_add_unfused(o.coef, phi, Wm[idx]);
+                        const int col = k * AW + (TDPRED ? 0 : o.act);
+                        if (pe_smem) {
+                            R* wp = Wpe + (size_t)col * BLOCK + tid;
+                            *wp = O::mul_add_unfused(o.coef, phi, *wp);
+                        } else {
+                            const int64_t idx = (int64_t)col * N + i;
+                            Wm[idx] = O::mul_add_unfused(o.coef, phi, Wm[idx]);
+                        }
                     });
                 }
                 if (TRACE) {
@@ -469,6 +484,10 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         a.actions[i] = act;
 #pragma unroll
         for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
+    }
+    if (pe_smem && active) {
+        R* Wm = static_cast<R*>(a.W);
+        for (int j = 0; j < FA; ++j) Wm[(int64_t)j * N + i] = Wpe[(size_t)j * BLOCK + tid];
     }
     if (TRACE && active) {
         R* Z = static_cast<R*>(a.z);
