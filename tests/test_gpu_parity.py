@@ -615,3 +615,21 @@ def test_cpp_mirror_example_matches_oracle(E, oracle):
     assert n_ep[0] == 3 and int(h[0]) == want and last_len[0] == lengths[-1]
     norm = float(re.search(r"\|W\|\^2 = (\S+)", out.stdout).group(1))
     assert abs(norm - float((o.weights() ** 2).sum())) < 1e-12 * max(1.0, norm)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: in-kernel dW exchange over NVLink peer memory (needs >= 2 GPUs on the box; skipped otherwise)
+# ---------------------------------------------------------------------------------------------
+def test_multi_gpu_peer_exchange_matches_single_gpu(E):
+    import os
+    import subprocess
+    import sys
+    n = abi.load().rsrl_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2 if n < 4 else 4
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "multi_gpu_check.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
