@@ -633,3 +633,90 @@ def test_multi_gpu_peer_exchange_matches_single_gpu(E):
                           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "multi_gpu_check.py")],
                          capture_output=True, text=True, timeout=900)
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# ragged / extreme shapes of the persistent kernel and error behaviour of the ABI
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 33, 449, 1000, 2049])
+@pytest.mark.parametrize("mode", [abi.SHARED, abi.PER_ENV], ids=["shared", "per_env"])
+def test_ragged_env_counts(E, oracle, n, mode):
+    """1 .. 17 CTAs, partially filled warps and leader groups of unequal size must not change the result."""
+    cfg = _mc_cfg(n_envs=n, weight_mode=mode, policy=abi.EPSILON_GREEDY, epsilon=0.1, max_episode_steps=40,
+                  update_scale=abi.SCALE_MEAN)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        for chunk in (1, 2, 60):
+            e.step(chunk)
+            o.step(chunk)
+        e.sync()
+        _compare_engines(e, o, w_tol=1e-9)
+
+
+def test_more_envs_than_resident_threads(E, oracle):
+    """N > 148 x 512: every thread of the persistent kernel loops over several envs per step (state through L2)."""
+    cfg = _mc_cfg(n_envs=100003, max_episode_steps=3, update_scale=abi.SCALE_MEAN, record_td_error=0)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(5)
+        o.step(5)
+        e.sync()
+        assert (e.actions() == o.actions()).all() and (e.episode_steps() == o.episode_steps()).all()
+        assert np.abs(e.states() - o.states()).max() < 1e-12 and np.abs(e.weights() - o.weights()).max() < 1e-10
+        assert e.stats()["total_episodes"] == o.stats()["total_episodes"] == 100003
+
+
+def test_dutch_trace_and_epsilon_schedule(E, oracle):
+    """Dutch traces (traces.rs:222-240) and the per-episode epsilon decay of examples/sarsa_lambda.rs:68."""
+    cfg = _mc_cfg(algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99,
+                  trace_rule=abi.TRACE_DUTCH, n_envs=48, max_episode_steps=60)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        eps = 0.2
+        for _ in range(5):
+            e.step(60)
+            o.step(60)
+            eps *= 0.995
+            e.set_epsilon(eps)
+            o.set_epsilon(eps)
+        e.sync()
+        _compare_engines(e, o, w_tol=1e-9)
+        assert np.abs(e.traces() - o.traces()).max() < 1e-9
+
+
+def test_error_behaviour(E):
+    import ctypes as C
+    lib = abi.load()
+    cfg = _mc_cfg(n_envs=8, record_td_error=0)
+    with E.Engine(cfg) as e:
+        s = e.states()
+        a = np.zeros(8, dtype=np.int32)
+        with pytest.raises(abi.RsrlError) as ei:
+            e.handle(s, a + 7, np.zeros(8), s, np.zeros(8, dtype=np.uint8))
+        assert ei.value.code == abi.EINVAL and "action" in str(ei.value)
+        with pytest.raises(abi.RsrlError) as ei:
+            e.traces()
+        assert ei.value.code == abi.EINVAL
+        with pytest.raises(abi.RsrlError) as ei:
+            e.td_errors()
+        assert ei.value.code == abi.EINVAL
+        assert lib.rsrl_engine_step(e.h, -1) == abi.EINVAL
+        assert lib.rsrl_engine_evaluate(e.h, 0, abi.dp(s), abi.dp(np.zeros(3))) == abi.EINVAL
+        with pytest.raises(abi.RsrlError) as ei:
+            e.set_epsilon(-0.5)
+        assert ei.value.code == abi.EINVAL
+    with pytest.raises(abi.RsrlError) as ei:
+        E.Engine(_mc_cfg(n_envs=0))
+    assert ei.value.code == abi.EINVAL
+    with pytest.raises(abi.RsrlError) as ei:   # per-env weights: transition i belongs to agent i
+        with E.Engine(_mc_cfg(n_envs=8, weight_mode=abi.PER_ENV)) as e2:
+            e2.handle(np.zeros((3, 2)), np.zeros(3, dtype=np.int32), np.zeros(3), np.zeros((3, 2)), np.zeros(3, dtype=np.uint8))
+    assert ei.value.code == abi.EINVAL
+    with pytest.raises(abi.RsrlError) as ei:   # NaN weights: the reference panics, the engine reports it at sync
+        with E.Engine(_mc_cfg(n_envs=8)) as e3:
+            e3.set_weights(np.full((36, 3), np.nan))
+            e3.step(1)
+            e3.sync()
+    assert ei.value.code == abi.ENONFINITE
+    r, t = np.zeros(1), np.zeros(1, dtype=np.uint8)
+    assert lib.rsrl_domain_step(9, 1, abi.dp(np.zeros((1, 2))), abi.ip(np.zeros(1, dtype=np.int32)), abi.dp(r), abi.u8p(t)) == abi.EINVAL
