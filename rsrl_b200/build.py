@@ -14,11 +14,15 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 HEADERS = ["device.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
 
 
+# headers only some translation units include (kept out of HEADERS so that editing them does not rebuild everything)
+EXTRA_DEPS = {"abi.cu": ["f4tc_launch.h"], "f4tc_inst.cu": ["f4tc_launch.h", "f4tc.cuh"]}
+
+
 def _units():
     # RSRL_BUILD_DOMAINS=0 (development only) leaves the CartPole / Acrobot instantiations out for fast iteration;
     # the default builds everything.
     doms = {int(d) for d in os.environ.get("RSRL_BUILD_DOMAINS", "0,1,2").split(",")}
-    units = [("abi.o", "abi.cu", [])]
+    units = [("abi.o", "abi.cu", []), ("f4tc.o", "f4tc_inst.cu", [])]
     for rname, rtype in (("f32", "float"), ("f64", "double")):
         units.append((f"tile_{rname}.o", "tile_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
         units.append((f"f4_{rname}.o", "f4_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
@@ -46,7 +50,8 @@ def build(force=False, verbose=False):
     jobs = []
     for obj, src, defs in _units():
         o, s = os.path.join(OBJ, obj), os.path.join(CSRC, src)
-        if force or _stale(o, [s] + hdrs):
+        extra = [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(src, [])]
+        if force or _stale(o, [s] + hdrs + extra):
             jobs.append([NVCC] + FLAGS + defs + ["-c", s, "-o", o])
 
     def run(cmd):

@@ -12,6 +12,7 @@
 #include "launch.h"
 #include "tile.cuh"
 #include "fourier4.cuh"
+#include "f4tc_launch.h"
 
 using namespace rsrl;
 
@@ -199,6 +200,8 @@ struct rsrl_engine {
     bool f4 = false;
     F4Args f4args = {nullptr, nullptr};
     int f4_nseg = 0;
+    // tcgen05 path (f4tc.cuh): bit 0 = env kernel, bit 1 = dW kernel (RSRL_B200_F4TC, default 3; order 7, f32)
+    int f4tc = 0, f4tc_env_grid = 0, f4tc_dw_grid = 0;
     // TileCoding engines (tile.cuh)
     bool tile = false;
     TileArgs targs;
@@ -347,14 +350,27 @@ static int finish_shared_step(rsrl_engine* e, int n_blocks) {
 
 static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
     const bool f32 = e->cfg.dtype == RSRL_F32;
-    const int grid = (int)((n + e->block - 1) / e->block);
-    cudaError_t ce = (f32 ? launch_f4_env_f32 : launch_f4_env_f64)(e->cfg.domain, e->cfg.basis_order, ext, a, e->f4args, grid, e->block, e->smem, e->stream);
+    cudaError_t ce;
+    if (e->f4tc & 1) {
+        const int n_tiles = (int)((n + 127) / 128);
+        ce = launch_f4tc_env(e->cfg.domain, ext, a, e->f4args, n_tiles, n_tiles < e->f4tc_env_grid ? n_tiles : e->f4tc_env_grid, e->stream);
+    } else {
+        const int grid = (int)((n + e->block - 1) / e->block);
+        ce = (f32 ? launch_f4_env_f32 : launch_f4_env_f64)(e->cfg.domain, e->cfg.basis_order, ext, a, e->f4args, grid, e->block, e->smem, e->stream);
+    }
     if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(&e->cfg); }
     CU_TRY(ce);
-    int nseg = e->f4_nseg;
-    const int64_t max_seg = (n + 63) / 64;
-    if (nseg > max_seg) nseg = (int)max_seg;
-    CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->stream));
+    int nseg;
+    if (e->f4tc & 2) {
+        const int64_t n_sub = (n + 31) / 32;
+        nseg = (int)(n_sub < e->f4tc_dw_grid ? n_sub : e->f4tc_dw_grid);
+        CU_TRY(launch_f4tc_dw(e->cfg.domain, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->counters, e->stream));
+    } else {
+        nseg = e->f4_nseg;
+        const int64_t max_seg = (n + 63) / 64;
+        if (nseg > max_seg) nseg = (int)max_seg;
+        CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->stream));
+    }
     e->launches += 2;
     return finish_shared_step(e, nseg);
 }
@@ -455,6 +471,11 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         const int64_t max_seg = (e->N + 63) / 64;
         if (e->f4_nseg > max_seg) e->f4_nseg = (int)max_seg;
         if (e->f4_nseg < 1) e->f4_nseg = 1;
+        if (cfg->dtype == RSRL_F32 && cfg->basis_order == 7) {
+            e->f4tc = getenv("RSRL_B200_F4TC") ? atoi(getenv("RSRL_B200_F4TC")) & 3 : 3;
+            e->f4tc_env_grid = sms;
+            e->f4tc_dw_grid = sms;
+        }
     } else if (e->tile) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -499,7 +520,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     } else if (e->f4) {
         E_TRY(cudaMalloc(&e->f4args.from_states, N * 4 * sizeof(double)));
         E_TRY(cudaMalloc(&e->f4args.coef, N * e->rsz));
-        E_TRY(cudaMalloc(&e->partials, (size_t)e->f4_nseg * e->FA * e->rsz));
+        E_TRY(cudaMalloc(&e->partials, (size_t)(e->f4_nseg > e->f4tc_dw_grid ? e->f4_nseg : e->f4tc_dw_grid) * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     } else if (cfg->weight_mode == RSRL_SHARED) {
         E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
@@ -648,6 +669,7 @@ int rsrl_engine_sync(rsrl_engine_t* e) {
     CU_TRY(cudaStreamSynchronize(e->stream));
     Counters c;
     CU_TRY(cudaMemcpy(&c, e->counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.pad) return fail(RSRL_ECUDA, "tensor-core pipeline fault: a tcgen05 completion barrier timed out (f4tc.cuh)");
     if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum (NaN weights); the reference panics in utils.rs:76");
     return RSRL_OK;
 }
@@ -1095,6 +1117,7 @@ static int policy_call(int mode, int32_t policy, double eps, uint64_t seed, uint
     else CU_TRY(cudaMemcpy(act_out, dout.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     Counters c;
     CU_TRY(cudaMemcpy(&c, dc.p, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.pad) return fail(RSRL_ECUDA, "tensor-core pipeline fault: a tcgen05 completion barrier timed out (f4tc.cuh)");
     if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum; the reference panics in utils.rs:76");
     return RSRL_OK;
 }

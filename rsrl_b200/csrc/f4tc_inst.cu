@@ -1,0 +1,49 @@
+// f4tc_inst.cu — instantiations + host launchers of the tcgen05 path (f4tc.cuh): order-7 Fourier, 4-D domains, f32
+#include "f4tc_launch.h"
+#include "f4tc.cuh"
+
+namespace rsrl {
+
+template <int DOM, bool EXT>
+static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
+    auto kern = f4tc_env_kernel<DOM, EXT>;
+    constexpr size_t smem = F4tcEnvSmem<Domain<DOM>::A>::bytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, 128, smem, st>>>(a, fa, n_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_f4tc_env(int domain, bool ext, const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
+    if (domain == RSRL_CART_POLE) return ext ? env_one<RSRL_CART_POLE, true>(a, fa, n_tiles, grid, st) : env_one<RSRL_CART_POLE, false>(a, fa, n_tiles, grid, st);
+    if (domain == RSRL_ACROBOT) return ext ? env_one<RSRL_ACROBOT, true>(a, fa, n_tiles, grid, st) : env_one<RSRL_ACROBOT, false>(a, fa, n_tiles, grid, st);
+    return cudaErrorInvalidDeviceFunction;
+}
+
+template <int DOM>
+static cudaError_t dw_one(int64_t n, const double* from_states, const void* coef, const int32_t* actions, int grid, void* partials,
+                          Counters* counters, cudaStream_t st) {
+    auto kern = f4tc_dw_kernel<DOM>;
+    constexpr size_t smem = F4tcDwSmem<Domain<DOM>::A>::bytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, 256, smem, st>>>(n, from_states, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_f4tc_dw(int domain, int64_t n, const double* from_states, const void* coef, const int32_t* actions, int grid,
+                           void* partials, Counters* counters, cudaStream_t st) {
+    if (domain == RSRL_CART_POLE) return dw_one<RSRL_CART_POLE>(n, from_states, coef, actions, grid, partials, counters, st);
+    if (domain == RSRL_ACROBOT) return dw_one<RSRL_ACROBOT>(n, from_states, coef, actions, grid, partials, counters, st);
+    return cudaErrorInvalidDeviceFunction;
+}
+
+}  // namespace rsrl

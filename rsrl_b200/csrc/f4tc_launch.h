@@ -1,0 +1,9 @@
+// f4tc_launch.h — host launchers of the tcgen05 path of the order-7 Fourier basis (f4tc.cuh), f32 only
+#pragma once
+#include "launch.h"
+
+namespace rsrl {
+cudaError_t launch_f4tc_env(int domain, bool ext, const StepArgs&, const F4Args&, int n_tiles, int grid, cudaStream_t);
+cudaError_t launch_f4tc_dw(int domain, int64_t n, const double* from_states, const void* coef, const int32_t* actions, int grid,
+                           void* partials, Counters* counters, cudaStream_t);
+}  // namespace rsrl
