@@ -336,7 +336,8 @@ static cudaError_t launch_add(rsrl_engine* e) {
 
 // after a SHARED-mode fused launch: partials -> dW (-> allreduce) -> W
 static int finish_shared_step(rsrl_engine* e, int n_blocks) {
-    CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks) : launch_reduce<double>(e, n_blocks));
+    if (e->f4tc) CU_TRY(launch_f4tc_reduce(e->partials, n_blocks, (int)e->FA, e->W, e->world > 1 ? e->dW : nullptr, e->stream));
+    else CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks) : launch_reduce<double>(e, n_blocks));
     e->launches += 1;
     if (e->world > 1) {
         ncclResult_t r = g_nccl.AllReduce(e->dW, e->dW, (size_t)e->FA, e->cfg.dtype == RSRL_F32 ? ncclFloat32 : ncclFloat64,
@@ -352,8 +353,8 @@ static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
     const bool f32 = e->cfg.dtype == RSRL_F32;
     cudaError_t ce;
     if (e->f4tc & 1) {
-        const int n_tiles = (int)((n + 127) / 128);
-        ce = launch_f4tc_env(e->cfg.domain, ext, a, e->f4args, n_tiles, n_tiles < e->f4tc_env_grid ? n_tiles : e->f4tc_env_grid, e->stream);
+        const int n_tiles = (int)((n + 127) / 128), n_pairs = (n_tiles + 1) / 2;  // a CTA runs two tiles at a time
+        ce = launch_f4tc_env(e->cfg.domain, ext, a, e->f4args, n_tiles, n_pairs < e->f4tc_env_grid ? n_pairs : e->f4tc_env_grid, e->stream);
     } else {
         const int grid = (int)((n + e->block - 1) / e->block);
         ce = (f32 ? launch_f4_env_f32 : launch_f4_env_f64)(e->cfg.domain, e->cfg.basis_order, ext, a, e->f4args, grid, e->block, e->smem, e->stream);

@@ -69,6 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fa
         if (mbar_try_wait(bar, parity)) return;
     atomicExch(fault, 1);
 }
+__device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -83,7 +84,31 @@ template <int COLS>
 __device__ __forceinline__ void tmem_free(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
 }
-// 32 lanes x 32 columns: thread `lane` of the warp receives row (lane base + lane), 32 consecutive fp32 columns
+// 32 lanes x 32 columns: thread `lane` of the warp receives row (lane base + lane), 32 consecutive fp32 columns.
+// tmem_ld32_issue only issues the load; the registers are valid after tmem_ld_wait() + tmem_ld_fence(r).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// pins the uses of r[] behind the wait (the compiler may not hoist arithmetic on them above this statement)
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -101,15 +126,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-// x = hi + lo with hi, lo TF32-representable (round to nearest, ties away): the tensor core then sees exact operands
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// x = hi + lo: hi = x rounded to TF32 (10 mantissa bits, half-up in magnitude: two integer ops), lo = x - hi exactly
+// (|lo| <= 2^-11 |x|; the tensor core drops lo's bits below 2^-10 |lo|, i.e. 2^-21 |x| at worst).
 __device__ __forceinline__ void split(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
 }
 
 }  // namespace tc
@@ -119,10 +140,11 @@ __device__ __forceinline__ void f4tc_e(const float (&tcs)[4][7], const float (&t
     re = c == 0 ? 1.0f : tcs[d][c - 1];
     im = c == 0 ? 0.0f : tsn[d][c - 1];
 }
-
 // ---------------------------------------------------------------------------------------------------------------
-// env kernel: Q(s_t), behaviour action, Domain::step, Q(s'), TD error -> coef / from_states / actions for the dW pass
-// CTA = 128 threads = 128 envs per tile (thread = env = GEMM row = TMEM lane), persistent over tiles.
+// env kernel: Q(s_t), behaviour action, Domain::step, Q(s'), TD error -> coef / from_states / actions for the dW pass.
+// CTA = 256 threads = two independent groups of 128; a group owns one tile of 128 envs at a time (thread = env = GEMM
+// row = TMEM lane), its own 32 KB operand buffer, 192 TMEM columns and one mbarrier; both groups share the W operand.
+// While one group generates operands / contracts its accumulator on the CUDA cores the other group's MMAs run.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW>
 struct F4tcEnvSmem {
@@ -133,30 +155,31 @@ struct F4tcEnvSmem {
 };
 
 template <int DOM, bool EXT>
-__global__ void __launch_bounds__(128, 1) f4tc_env_kernel(const StepArgs a, const F4Args fa, int n_tiles) {
+__global__ void __launch_bounds__(256, 1) f4tc_env_kernel(const StepArgs a, const F4Args fa, int n_tiles) {
     using Dom = Domain<DOM>;
     constexpr int D = 4, P = 7, AW = Dom::A;
     using SM = F4tcEnvSmem<AW>;
     constexpr int NB = SM::NB;
     constexpr uint32_t A_LBO = 16 * 128, B_LBO = (NB / 8) * 128, SBO = 128;
     constexpr uint32_t IDESC = tc::make_idesc(128, NB);
-    constexpr int TMEM_COLS = 512;  // two accumulators of NB (<= 192) columns
+    constexpr int TMEM_COLS = 512;  // group g accumulates in columns [256 g, 256 g + NB)
     static_assert(Dom::D == 4, "4-D domains only");
 
     extern __shared__ __align__(128) unsigned char f4tc_smem[];
     float* Bhi = reinterpret_cast<float*>(f4tc_smem);
     float* Blo = Bhi + SM::B_FLOATS;
-    float* Aun = Blo + SM::B_FLOATS;  // unit buffer ub: hi = Aun + ub * 2 * UNIT_FLOATS, lo = hi + UNIT_FLOATS
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, gwarp = gt >> 5;
+    float* Ahi = Blo + SM::B_FLOATS + grp * 2 * SM::UNIT_FLOATS;
+    float* Alo = Ahi + SM::UNIT_FLOATS;
     int* fault = &a.counters->pad;
 
     // ---- one-time setup: W -> B operand (row n = a*64 + i, column j), TMEM, barriers ----
     {
         const float* Wg = static_cast<const float*>(a.W);
-        for (int idx = tid; idx < 4096 * AW; idx += 128) {
+        for (int idx = tid; idx < 4096 * AW; idx += 256) {
             const int k = idx / AW, c = idx - k * AW;
             const int i = k >> 6, j = k & 63, n = c * 64 + i;
             float hi, lo;
@@ -166,7 +189,7 @@ __global__ void __launch_bounds__(128, 1) f4tc_env_kernel(const StepArgs a, cons
             Blo[o] = lo;
         }
     }
-    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(&tmem_slot);
+    if (tid < 32) tc::tmem_alloc<TMEM_COLS>(&tmem_slot);
     if (tid == 0) {
         tc::mbar_init(tc::smem_u32(&bars[0]), 1);
         tc::mbar_init(tc::smem_u32(&bars[1]), 1);
@@ -176,104 +199,114 @@ __global__ void __launch_bounds__(128, 1) f4tc_env_kernel(const StepArgs a, cons
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    uint32_t ph0 = 0, ph1 = 0;  // phase parity of bars[0], bars[1] (uniform over the CTA)
+    const uint32_t acc = tmem_slot + (uint32_t)(grp * 256);
+    const uint32_t acc_lane = acc + ((uint32_t)(gwarp * 32) << 16);
+    const uint32_t bar = tc::smem_u32(&bars[grp]);
+    uint32_t ph = 0;  // phase parity of the group's barrier (uniform over the group)
+    const int a_row = (gt >> 3) * 32 + (gt & 7) * 4;  // float offset of the thread's row inside a 16-byte K chunk column
 
-    struct Tab { float c[4][P], s[4][P]; };
+    float tcs[4][P], tsn[4][P];  // tables of the state being evaluated
 
-    // Q(state of tab) for the thread's env; all 128 threads must call (block-level barriers inside)
-    auto qeval = [&](const Tab& tb, float* q) {
+    // unit (part, kh): values of row gt, k = (i2 - 4 kh) * 8 + i3
+    auto unit_compute = [&](int part, int kh, float (&hi)[32], float (&lo)[32]) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int part = u >> 1, kh = u & 1, ub = u & 1;
-            float* Ahi = Aun + ub * 2 * SM::UNIT_FLOATS;
-            float* Alo = Ahi + SM::UNIT_FLOATS;
-            if (u >= 2) {  // the MMAs of unit u-2 have finished reading this buffer
-                if (ub == 0) { tc::mbar_wait(tc::smem_u32(&bars[0]), ph0, fault); ph0 ^= 1; }
-                else { tc::mbar_wait(tc::smem_u32(&bars[1]), ph1, fault); ph1 ^= 1; }
-            }
-            // generate the unit: row = tid, k = (i2 - 4*kh)*8 + i3, value = part of e2[c2] * e3[c3]
+        for (int i2l = 0; i2l < 4; ++i2l) {
+            float e2r, e2i;
+            f4tc_e(tcs, tsn, 2, P - (kh * 4 + i2l), e2r, e2i);
 #pragma unroll
-            for (int i2l = 0; i2l < 4; ++i2l) {
-                const int c2 = P - (kh * 4 + i2l);
-                float e2r, e2i;
-                f4tc_e(tb.c, tb.s, 2, c2, e2r, e2i);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const int c3 = P - (g * 4 + x);
-                        float e3r, e3i;
-                        f4tc_e(tb.c, tb.s, 3, c3, e3r, e3i);
-                        const float v = part == 0 ? fmaf(e2r, e3r, -(e2i * e3i)) : fmaf(e2r, e3i, e2i * e3r);
-                        tc::split(v, hi[x], lo[x]);
-                    }
-                    const int kc = i2l * 2 + g;  // 16-byte K chunk
-                    const int o = kc * (A_LBO / 4) + (tid >> 3) * 32 + (tid & 7) * 4;
-                    *reinterpret_cast<float4*>(Ahi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(Alo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                }
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc::fence_after_sync();
-                const uint32_t acc = tmem + (uint32_t)(part * NB);
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t abase = tc::smem_u32(pass == 1 ? Alo : Ahi);
-                    const uint32_t bbase = tc::smem_u32(pass == 2 ? Blo : Bhi) + (uint32_t)kh * 8u * B_LBO;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc::umma_tf32(acc, tc::make_desc(abase + ks * 2 * A_LBO, A_LBO, SBO), tc::make_desc(bbase + ks * 2 * B_LBO, B_LBO, SBO),
-                                      IDESC, (kh | pass | ks) != 0 ? 1u : 0u);
-                }
-                tc::umma_commit(tc::smem_u32(&bars[ub]));
+            for (int i3 = 0; i3 < 8; ++i3) {
+                float e3r, e3i;
+                f4tc_e(tcs, tsn, 3, P - i3, e3r, e3i);
+                const float v = part == 0 ? fmaf(e2r, e3r, -(e2i * e3i)) : fmaf(e2r, e3i, e2i * e3r);
+                tc::split(v, hi[i2l * 8 + i3], lo[i2l * 8 + i3]);
             }
         }
+    };
+    auto unit_store = [&](const float (&hi)[32], const float (&lo)[32]) {
 #pragma unroll
-        for (int c = 0; c < AW; ++c) q[c] = 0.0f;
-        // epilogue: q_a = sum_i ur_i Pr[a*64 + i] - ui_i Pi[a*64 + i], i = i0*8 + i1
-        auto contract = [&](int part) {
-            const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(part * NB);
-            __syncwarp();  // tcgen05.ld is .sync.aligned: thread 0 rejoins its warp after issuing the MMAs
+        for (int kc = 0; kc < 8; ++kc) {
+            const int o = kc * (A_LBO / 4) + a_row;
+            *reinterpret_cast<float4*>(Ahi + o) = make_float4(hi[kc * 4], hi[kc * 4 + 1], hi[kc * 4 + 2], hi[kc * 4 + 3]);
+            *reinterpret_cast<float4*>(Alo + o) = make_float4(lo[kc * 4], lo[kc * 4 + 1], lo[kc * 4 + 2], lo[kc * 4 + 3]);
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        tc::group_sync(1 + grp, 128);
+    };
+    auto unit_issue = [&](int kh) {  // 3xTF32: hi*hi + lo*hi + hi*lo over the unit's 4 K steps
+        if (gt == 0) {
+            tc::fence_after_sync();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float uu[32];
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t abase = tc::smem_u32(pass == 1 ? Alo : Ahi);
+                const uint32_t bbase = tc::smem_u32(pass == 2 ? Blo : Bhi) + (uint32_t)kh * 8u * B_LBO;
 #pragma unroll
-                for (int i0l = 0; i0l < 4; ++i0l) {
-                    float e0r, e0i;
-                    f4tc_e(tb.c, tb.s, 0, P - (h * 4 + i0l), e0r, e0i);
+                for (int ks = 0; ks < 4; ++ks)
+                    tc::umma_tf32(acc, tc::make_desc(abase + ks * 2 * A_LBO, A_LBO, SBO), tc::make_desc(bbase + ks * 2 * B_LBO, B_LBO, SBO), IDESC,
+                                  (kh | pass | ks) != 0 ? 1u : 0u);
+            }
+            tc::umma_commit(bar);
+        }
+    };
+    auto unit_wait = [&]() { tc::mbar_wait(bar, ph, fault); ph ^= 1; };
+    // q_a += sum_i u_i P[a*64 + i]: u = Re(e0 e1) for the real part, -Im(e0 e1) for the imaginary part
+    auto contract = [&](int part, float* q) {
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the issuing thread rejoins its warp
+        tc::fence_after_sync();
 #pragma unroll
-                    for (int i1 = 0; i1 < 8; ++i1) {
-                        float e1r, e1i;
-                        f4tc_e(tb.c, tb.s, 1, P - i1, e1r, e1i);
-                        uu[i0l * 8 + i1] = part == 0 ? fmaf(e0r, e1r, -(e0i * e1i)) : -fmaf(e0r, e1i, e0i * e1r);
-                    }
-                }
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[AW][32];
 #pragma unroll
-                for (int c = 0; c < AW; ++c) {
-                    float v[32];
-                    tc::tmem_ld32(acc + (uint32_t)(c * 64 + h * 32), v);
+            for (int c = 0; c < AW; ++c) tc::tmem_ld32_issue(acc_lane + (uint32_t)(c * 64 + h * 32), r[c]);
+            float uu[32];
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) q[c] = fmaf(uu[x], v[x], q[c]);
+            for (int i0l = 0; i0l < 4; ++i0l) {
+                float e0r, e0i;
+                f4tc_e(tcs, tsn, 0, P - (h * 4 + i0l), e0r, e0i);
+#pragma unroll
+                for (int i1 = 0; i1 < 8; ++i1) {
+                    float e1r, e1i;
+                    f4tc_e(tcs, tsn, 1, P - i1, e1r, e1i);
+                    uu[i0l * 8 + i1] = part == 0 ? fmaf(e0r, e1r, -(e0i * e1i)) : -fmaf(e0r, e1i, e0i * e1r);
                 }
             }
-        };
-        // units 0,1 (the real-part accumulator) were waited for above (u = 3): contract them while units 2,3 run
-        tc::fence_after_sync();
-        contract(0);
-        tc::mbar_wait(tc::smem_u32(&bars[0]), ph0, fault); ph0 ^= 1;  // unit 2 done
-        tc::mbar_wait(tc::smem_u32(&bars[1]), ph1, fault); ph1 ^= 1;  // unit 3 done
-        tc::fence_after_sync();
-        contract(1);
-        tc::fence_before_sync();  // the next call's MMAs overwrite the accumulators after its first __syncthreads
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < AW; ++c) {
+                tc::tmem_ld_fence(r[c]);
+#pragma unroll
+                for (int x = 0; x < 32; ++x) q[c] = fmaf(uu[x], __uint_as_float(r[c][x]), q[c]);
+            }
+        }
+        tc::fence_before_sync();  // orders these TMEM reads before the next unit_issue (after its group_sync)
+    };
+    // Q of the state whose tables are in tcs/tsn; every thread of the group must call
+    auto qeval = [&](float* q) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < AW; ++c) q[c] = 0.0f;
+        unit_compute(0, 0, hi, lo);
+        unit_store(hi, lo);
+        unit_issue(0);
+        unit_compute(0, 1, hi, lo);
+        unit_wait();
+        unit_store(hi, lo);
+        unit_issue(1);
+        unit_compute(1, 0, hi, lo);
+        unit_wait();
+        contract(0, q);
+        unit_store(hi, lo);
+        unit_issue(0);
+        unit_compute(1, 1, hi, lo);
+        unit_wait();
+        unit_store(hi, lo);
+        unit_issue(1);
+        unit_wait();
+        contract(1, q);
     };
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = (int64_t)tile * 128 + tid;
+    for (int tile = blockIdx.x * 2 + grp; tile < n_tiles; tile += gridDim.x * 2) {
+        const int64_t i = (int64_t)tile * 128 + gt;
         const bool active = i < a.n;
         const uint64_t g = (uint64_t)(a.env_offset + (active ? i : 0));
         double s[D];
@@ -283,58 +316,54 @@ __global__ void __launch_bounds__(128, 1) f4tc_env_kernel(const StepArgs a, cons
 #pragma unroll
             for (int d = 0; d < D; ++d) fa.from_states[i * D + d] = s[d];
         }
-        Tab tab;
-        f4_tables<float, Dom, P, RSRL_FOURIER>(s, tab.c, tab.s);
-
-        // ---- B: behaviour action and Q(s_t, a_t) under W_t (kernels.cuh:env_core) ----
-        float q[AW];
-        qeval(tab, q);
-        bool nonfinite = false;
-        int act;
-        if (EXT) act = active ? a.ext_actions[i] : 0;
-        else act = policy_sample<float, AW>(a.pol, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
-        float qsa = q[0];
+        bool nonfinite = false, terminated = false;
+        int act = 0;
+        float qsa = 0.0f, residual = 0.0f;
+        double reward = 0.0;
+#pragma unroll 1
+        for (int ev = 0; ev < 2; ++ev) {
+            f4_tables<float, Dom, P, RSRL_FOURIER>(s, tcs, tsn);
+            float q[AW];
+            qeval(q);
+            if (ev == 0) {
+                // ---- B: behaviour action and Q(s_t, a_t) under W_t (kernels.cuh:env_core) ----
+                if (EXT) act = active ? a.ext_actions[i] : 0;
+                else act = policy_sample<float, AW>(a.pol, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
+                qsa = q[0];
 #pragma unroll
-        for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
-
-        // ---- C: Domain::transition ----
-        double reward;
-        bool terminated;
-        if (EXT) {
-            if (active) {
+                for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
+                // ---- C: Domain::transition ----
+                if (EXT) {
+                    if (active) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) s[d] = a.ext_to[i * D + d];
-            }
-            reward = active ? a.ext_rewards[i] : 0.0;
-            terminated = active ? a.ext_term[i] != 0 : false;
-        } else {
-            Dom::step(s, act, reward, terminated);
-        }
-
-        // ---- D: TD error with W_t (Q(s') is evaluated for every row; terminal rows ignore it) ----
-        f4_tables<float, Dom, P, RSRL_FOURIER>(s, tab.c, tab.s);
-        float nq[AW];
-        qeval(tab, nq);
-        float residual;
-        if (terminated) {
-            residual = (float)reward - qsa;
-        } else {
-            float target;
-            if (a.algo == RSRL_QLEARNING || a.algo == RSRL_Q_LAMBDA) {
-                find_max<float, AW>(nq, target);
-            } else if (a.algo == RSRL_SARSA || a.algo == RSRL_SARSA_LAMBDA) {
-                const int na = policy_sample<float, AW>(a.pol, nq, g, a.t, STREAM_TARGET, nonfinite);
-                target = nq[0];
-#pragma unroll
-                for (int c = 0; c < AW; ++c) if (c == na) target = nq[c];
+                        for (int d = 0; d < D; ++d) s[d] = a.ext_to[i * D + d];
+                        reward = a.ext_rewards[i];
+                        terminated = a.ext_term[i] != 0;
+                    }
+                } else {
+                    Dom::step(s, act, reward, terminated);
+                }
+            } else if (terminated) {
+                // ---- D: TD error with W_t (Q(s') is evaluated for every row; terminal rows ignore it) ----
+                residual = (float)reward - qsa;
             } else {
-                float p[AW];
-                policy_probs<float, AW>(a.pol.policy, (float)a.epsilon, nq, p);
-                target = 0.0f;
+                float target;
+                if (a.algo == RSRL_QLEARNING || a.algo == RSRL_Q_LAMBDA) {
+                    find_max<float, AW>(q, target);
+                } else if (a.algo == RSRL_SARSA || a.algo == RSRL_SARSA_LAMBDA) {
+                    const int na = policy_sample<float, AW>(a.pol, q, g, a.t, STREAM_TARGET, nonfinite);
+                    target = q[0];
 #pragma unroll
-                for (int c = 0; c < AW; ++c) target = target + nq[c] * p[c];
+                    for (int c = 0; c < AW; ++c) if (c == na) target = q[c];
+                } else {
+                    float p[AW];
+                    policy_probs<float, AW>(a.pol.policy, (float)a.epsilon, q, p);
+                    target = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < AW; ++c) target = target + q[c] * p[c];
+                }
+                residual = (float)reward + (float)a.gamma * target - qsa;
             }
-            residual = (float)reward + (float)a.gamma * target - qsa;
         }
         const float coef = a.algo == RSRL_EXPECTED_SARSA ? (float)a.lr_scaled * ((float)a.alpha * residual) : (float)a.lr_scaled * residual;
 
@@ -353,14 +382,15 @@ __global__ void __launch_bounds__(128, 1) f4tc_env_kernel(const StepArgs a, cons
 
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_free<TMEM_COLS>(tmem);
+    if (tid < 32) tc::tmem_free<TMEM_COLS>(tmem_slot);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // dW kernel: partials[cta][k*AW + a] = sum over the CTA's envs of phi_k(s_env) * d_a(env), d_a = coef if a == action.
-// CTA = 256 threads; sub-tile = 32 envs; thread = (env lane, q = warp): A rows m = q*16 + i1*2 + b (i0 = q),
-// B rows n = a*32 + i2'*8 + q (i3 = q).  K index = (part, env): two units per sub-tile (real, imaginary), double-buffered
-// so that generating one unit overlaps the MMAs of the other.  The accumulator stays in TMEM for the whole kernel.
+// CTA = 512 threads; sub-tile = 32 envs; thread = (env lane, q = warp 0..15): A rows m = i0*16 + i1*2 + b with
+// i0 = q/2, i1 in 4(q%2)..+3; B rows n = a*32 + i2'*8 + i3 with i3 = q/2, i2' in 2(q%2)..+1.  K index = (part, env):
+// two units per sub-tile (real, imaginary), double-buffered so that generating one unit overlaps the MMAs of the other.
+// The accumulator stays in TMEM for the whole kernel.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW>
 struct F4tcDwSmem {
@@ -375,7 +405,7 @@ struct F4tcDwSmem {
 };
 
 template <int DOM>
-__global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double* __restrict__ from_states, const float* __restrict__ coef,
+__global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double* __restrict__ from_states, const float* __restrict__ coef,
                                                          const int32_t* __restrict__ actions, float* __restrict__ partials, Counters* counters) {
     using Dom = Domain<DOM>;
     constexpr int P = 7, AW = Dom::A;
@@ -393,7 +423,7 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5, qi = q >> 1, hq = q & 1;
     int* fault = &counters->pad;
 
     if (q == 0) tc::tmem_alloc<TMEM_COLS>(&tmem_slot);
@@ -412,6 +442,11 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
     uint32_t ph[2] = {0, 0};
     bool used[2] = {false, false};
     bool first_mma = true;
+    // float offsets of this thread's element (k = lane) in its rows
+    const int ka = (lane >> 2) * (int)(SM::A_LBO / 4) + (lane & 3);
+    const int kb = (lane >> 2) * (int)(SM::B_LBO / 4) + (lane & 3);
+    const int m0 = qi * 16 + hq * 8;  // rows m0 .. m0+7 = (i1 = 4 hq + r/2, b = r%2): one 8-row group
+    const int oa = ka + (m0 >> 3) * 32;
 
     for (int64_t st = s_begin; st < s_end; ++st) {
         const int64_t env = st * 32 + lane;
@@ -442,34 +477,32 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
             re = c == 0 ? 1.0f : tabs[(d * 7 + c - 1) * 64 + lane];
             im = c == 0 ? 0.0f : tabs[(d * 7 + c - 1) * 64 + 32 + lane];
         };
-        // u_m = e0[7-q] * e1[7-i1] * (b == 0 ? e2[4] : 1), m = q*16 + i1*2 + b
-        float ur[16], ui[16];
+        // u_m = e0[7-i0] * e1[7-i1] * (b == 0 ? e2[4] : 1), rows r = (i1 - 4 hq)*2 + b
+        float ur[8], ui[8];
         {
             float e0r, e0i, e24r, e24i;
-            E(0, P - q, e0r, e0i);
+            E(0, P - qi, e0r, e0i);
             E(2, 4, e24r, e24i);
 #pragma unroll
-            for (int i1 = 0; i1 < 8; ++i1) {
+            for (int i1l = 0; i1l < 4; ++i1l) {
                 float e1r, e1i;
-                E(1, P - i1, e1r, e1i);
-                float tr, ti;
-                if (i1 == 7) { tr = e0r; ti = e0i; }
-                else { tr = fmaf(e0r, e1r, -(e0i * e1i)); ti = fmaf(e0r, e1i, e0i * e1r); }
-                ur[i1 * 2 + 1] = tr; ui[i1 * 2 + 1] = ti;                                            // b = 1: c2 high part 0
-                ur[i1 * 2] = fmaf(tr, e24r, -(ti * e24i)); ui[i1 * 2] = fmaf(tr, e24i, ti * e24r);   // b = 0: times e2[4]
+                E(1, P - (hq * 4 + i1l), e1r, e1i);
+                const float tr = fmaf(e0r, e1r, -(e0i * e1i)), ti = fmaf(e0r, e1i, e0i * e1r);
+                ur[i1l * 2 + 1] = tr; ui[i1l * 2 + 1] = ti;                                            // b = 1: c2 high part 0
+                ur[i1l * 2] = fmaf(tr, e24r, -(ti * e24i)); ui[i1l * 2] = fmaf(tr, e24i, ti * e24r);   // b = 0: times e2[4]
             }
         }
-        // v_n' = e2[3-i2'] * e3[7-q], n' = i2'*8 + q
-        float vr[4], vi[4];
+        // v_n' = e2[3-i2'] * e3[7-i3], i3 = qi, i2' = 2 hq + x
+        float vr[2], vi[2];
         {
             float e3r, e3i;
-            E(3, P - q, e3r, e3i);
+            E(3, P - qi, e3r, e3i);
 #pragma unroll
-            for (int i2l = 0; i2l < 4; ++i2l) {
+            for (int x = 0; x < 2; ++x) {
                 float e2r, e2i;
-                E(2, 3 - i2l, e2r, e2i);
-                if (i2l == 3) { vr[i2l] = e3r; vi[i2l] = e3i; }
-                else { vr[i2l] = fmaf(e2r, e3r, -(e2i * e3i)); vi[i2l] = fmaf(e2r, e3i, e2i * e3r); }
+                E(2, 3 - (hq * 2 + x), e2r, e2i);
+                vr[x] = fmaf(e2r, e3r, -(e2i * e3i));
+                vi[x] = fmaf(e2r, e3i, e2i * e3r);
             }
         }
         const float dc = dco[lane];
@@ -483,24 +516,20 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
             float* Blo = Bhi + SM::B_FLOATS;
             if (used[part]) { tc::mbar_wait(tc::smem_u32(&bars[part]), ph[part], fault); ph[part] ^= 1; }
             used[part] = true;
-            const int ko = (lane >> 2) * (int)(SM::A_LBO / 4) + (lane & 3);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const int m = q * 16 + r;
+            for (int r = 0; r < 8; ++r) {
                 float hi, lo;
                 tc::split(part == 0 ? ur[r] : ui[r], hi, lo);
-                const int o = ko + (m >> 3) * 32 + (m & 7) * 4;
-                Ahi[o] = hi;
-                Alo[o] = lo;
+                Ahi[oa + r * 4] = hi;
+                Alo[oa + r * 4] = lo;
             }
-            const int kb = (lane >> 2) * (int)(SM::B_LBO / 4) + (lane & 3);
 #pragma unroll
             for (int c = 0; c < AW; ++c)
 #pragma unroll
-                for (int i2l = 0; i2l < 4; ++i2l) {
-                    const int nrow = c * 32 + i2l * 8 + q;
+                for (int x = 0; x < 2; ++x) {
+                    const int nrow = c * 32 + (hq * 2 + x) * 8 + qi;
                     float hi = 0.0f, lo = 0.0f;
-                    if (c == act) tc::split(part == 0 ? vr[i2l] * dc : -(vi[i2l] * dc), hi, lo);
+                    if (c == act) tc::split(part == 0 ? vr[x] * dc : -(vi[x] * dc), hi, lo);
                     const int o = kb + (nrow >> 3) * 32 + (nrow & 7) * 4;
                     Bhi[o] = hi;
                     Blo[o] = lo;
@@ -529,7 +558,7 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
     // ---- drain + epilogue: TMEM [m = i0*16 + i1*2 + b][n = a*32 + i2'*8 + i3] -> partials[cta][k*AW + a] ----
     float* out = partials + (size_t)blockIdx.x * 4096 * AW;
     if (s_begin >= s_end) {
-        for (int j = tid; j < 4096 * AW; j += 256) out[j] = 0.0f;
+        for (int j = tid; j < 4096 * AW; j += 512) out[j] = 0.0f;
     } else {
 #pragma unroll
         for (int part = 0; part < 2; ++part)
@@ -554,6 +583,26 @@ __global__ void __launch_bounds__(256, 1) f4tc_dw_kernel(int64_t n, const double
     tc::fence_before_sync();
     __syncthreads();
     if (q == 0) tc::tmem_free<TMEM_COLS>(tmem);
+}
+
+// Fixed-order sum of the per-CTA partials: block = 8 warps x 32 consecutive weights; warp w adds partials w, w+8, ...
+// in ascending order, the 8 warp sums are added in warp order.  W += sum (single GPU) or dW_out = sum (exchange).
+__global__ void __launch_bounds__(256) f4tc_reduce_kernel(const float* __restrict__ partials, int n_partials, int fa, float* __restrict__ W,
+                                                          float* __restrict__ dW_out) {
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, j = blockIdx.x * 32 + lane;
+    float acc = 0.0f;
+    if (j < fa)
+        for (int p = w; p < n_partials; p += 8) acc += partials[(size_t)p * fa + j];
+    part[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && j < fa) {
+        float g = part[0][lane];
+#pragma unroll
+        for (int x = 1; x < 8; ++x) g += part[x][lane];
+        if (dW_out) dW_out[j] = g;
+        else W[j] += g;
+    }
 }
 
 }  // namespace rsrl

@@ -14,7 +14,7 @@ static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int n_tiles, int
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, 128, smem, st>>>(a, fa, n_tiles);
+    kern<<<grid, 256, smem, st>>>(a, fa, n_tiles);
     return cudaGetLastError();
 }
 
@@ -35,7 +35,7 @@ static cudaError_t dw_one(int64_t n, const double* from_states, const void* coef
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, 256, smem, st>>>(n, from_states, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters);
+    kern<<<grid, 512, smem, st>>>(n, from_states, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters);
     return cudaGetLastError();
 }
 
@@ -44,6 +44,12 @@ cudaError_t launch_f4tc_dw(int domain, int64_t n, const double* from_states, con
     if (domain == RSRL_CART_POLE) return dw_one<RSRL_CART_POLE>(n, from_states, coef, actions, grid, partials, counters, st);
     if (domain == RSRL_ACROBOT) return dw_one<RSRL_ACROBOT>(n, from_states, coef, actions, grid, partials, counters, st);
     return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t launch_f4tc_reduce(const void* partials, int n_partials, int fa, void* W, void* dW_out, cudaStream_t st) {
+    f4tc_reduce_kernel<<<(fa + 31) / 32, 256, 0, st>>>(static_cast<const float*>(partials), n_partials, fa, static_cast<float*>(W),
+                                                      static_cast<float*>(dW_out));
+    return cudaGetLastError();
 }
 
 }  // namespace rsrl
