@@ -198,7 +198,7 @@ struct rsrl_engine {
     double epsilon = 0.0;
     // large Fourier bases on the 4-D domains (fourier4.cuh): one env kernel + one dW kernel per batched step
     bool f4 = false;
-    F4Args f4args = {nullptr, nullptr};
+    F4Args f4args = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int f4_nseg = 0;
     // tcgen05 path (f4tc.cuh): bit 0 = env kernel, bit 1 = dW kernel (RSRL_B200_F4TC, default 3; order 7, f32)
     int f4tc = 0, f4tc_env_grid = 0, f4tc_dw_grid = 0;
@@ -365,14 +365,14 @@ static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
     if (e->f4tc & 2) {
         const int64_t n_sub = (n + 31) / 32;
         nseg = (int)(n_sub < e->f4tc_dw_grid ? n_sub : e->f4tc_dw_grid);
-        CU_TRY(launch_f4tc_dw(e->cfg.domain, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->counters, e->stream));
+        CU_TRY(launch_f4tc_dw(e->cfg.domain, n, e->f4args.tabs, e->f4args.coef, e->actions, nseg, e->partials, e->counters, e->phase_prof ? e->phase_prof + (size_t)e->pgrid * 8 : nullptr, e->stream));
     } else {
         nseg = e->f4_nseg;
         const int64_t max_seg = (n + 63) / 64;
         if (nseg > max_seg) nseg = (int)max_seg;
         CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->stream));
     }
-    e->launches += 2;
+    e->launches += e->f4tc ? 4 : 2;
     return finish_shared_step(e, nseg);
 }
 
@@ -413,22 +413,32 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (!e) return RSRL_OK;
     cudaSetDevice(e->cfg.device);
     if (e->phase_prof && e->t > 0) {
-        std::vector<long long> h((size_t)e->pgrid * 8);
+        std::vector<long long> h((size_t)e->pgrid * 16);
         cudaMemcpy(h.data(), e->phase_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        const char* names[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "LL exchange (thread 0)", "wait LL (bar)",
-                                "  LL: sum segs + publish 1", "  LL: leader hop-1 gather", "  LL: leader sum + publish 2"};
+        const char* names_d[8] = {"dW: inputs -> u, v (regs)", "dW: wait MMA (buffer free)", "dW: split + scalar stores", "dW: fence + __syncthreads",
+                                  "dW: MMA issue (thread 0)", "-", "-", "-"};
+        const char* names_p[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "LL exchange (thread 0)", "wait LL (bar)",
+                                  "  LL: sum segs + publish 1", "  LL: leader hop-1 gather", "  LL: leader sum + publish 2"};
+        const char* names_t[8] = {"load + tables", "unit compute (regs)", "wait MMA (mbarrier)", "contract (LDTM + FMA)", "store unit + sync + issue",
+                                  "TD + stores + bookkeeping", "issuer: MMA issue (pipe busy)", "issuer: idle (no unit ready)"};
+        const char** names = e->f4tc ? names_t : names_p;
         for (int q = 0; q < 8; ++q) {
             double sum = 0, mx = 0, mn = 1e30;
             int cntq = 0;
             for (int b2 = 0; b2 < e->pgrid; ++b2) { double v = (double)h[(size_t)b2 * 8 + q] / (double)e->t; if (v == 0) continue; ++cntq; sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
             fprintf(stderr, "[phase] %-28s cycles/step: mean %8.0f  min %8.0f  max %8.0f  (%d CTAs)\n", names[q], cntq ? sum / cntq : 0.0, mn, mx, cntq);
         }
+        for (int q = 0; e->f4tc && q < 5; ++q) {
+            double sum = 0;
+            for (int b2 = 0; b2 < e->pgrid; ++b2) sum += (double)h[(size_t)(e->pgrid + b2) * 8 + q] / (double)e->t;
+            fprintf(stderr, "[phase] %-28s cycles/step: mean %8.0f\n", names_d[q], sum / e->pgrid);
+        }
         cudaFree(e->phase_prof);
     }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef, e->f4args.tabs, e->f4args.q, e->f4args.aux, e->f4args.next_states};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -473,7 +483,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         if (e->f4_nseg > max_seg) e->f4_nseg = (int)max_seg;
         if (e->f4_nseg < 1) e->f4_nseg = 1;
         if (cfg->dtype == RSRL_F32 && cfg->basis_order == 7) {
-            e->f4tc = getenv("RSRL_B200_F4TC") ? atoi(getenv("RSRL_B200_F4TC")) & 3 : 3;
+            e->f4tc = getenv("RSRL_B200_F4TC") && atoi(getenv("RSRL_B200_F4TC")) == 0 ? 0 : 3;  // 0: CUDA-core path (development aid)
             e->f4tc_env_grid = sms;
             e->f4tc_dw_grid = sms;
         }
@@ -521,6 +531,12 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     } else if (e->f4) {
         E_TRY(cudaMalloc(&e->f4args.from_states, N * 4 * sizeof(double)));
         E_TRY(cudaMalloc(&e->f4args.coef, N * e->rsz));
+        if (e->f4tc) {
+            E_TRY(cudaMalloc(&e->f4args.tabs, N * 56 * sizeof(float)));
+            E_TRY(cudaMalloc(&e->f4args.q, N * 4 * sizeof(float)));
+            E_TRY(cudaMalloc(&e->f4args.aux, N * 4 * sizeof(float)));
+            E_TRY(cudaMalloc(&e->f4args.next_states, N * 4 * sizeof(double)));
+        }
         E_TRY(cudaMalloc(&e->partials, (size_t)(e->f4_nseg > e->f4tc_dw_grid ? e->f4_nseg : e->f4tc_dw_grid) * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     } else if (cfg->weight_mode == RSRL_SHARED) {
@@ -541,9 +557,10 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
-    if (getenv("RSRL_B200_PHASE_PROFILE") && e->persistent) {
-        E_TRY(cudaMalloc(&e->phase_prof, (size_t)e->pgrid * 8 * sizeof(long long)));
-        E_TRY(cudaMemset(e->phase_prof, 0, (size_t)e->pgrid * 8 * sizeof(long long)));
+    if (getenv("RSRL_B200_PHASE_PROFILE") && e->f4tc) e->pgrid = e->f4tc_env_grid;
+    if (getenv("RSRL_B200_PHASE_PROFILE") && (e->persistent || e->f4tc)) {
+        E_TRY(cudaMalloc(&e->phase_prof, (size_t)e->pgrid * 16 * sizeof(long long)));   // f4tc: second half = dW kernel
+        E_TRY(cudaMemset(e->phase_prof, 0, (size_t)e->pgrid * 16 * sizeof(long long)));
     }
     E_TRY(cudaMalloc(&e->init_bounds, 8 * sizeof(double)));
     // probe that the combination is built (fails loudly instead of at the first step)

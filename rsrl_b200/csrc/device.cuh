@@ -91,6 +91,7 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
     __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 0.6 : 0.07; }
     __host__ __device__ static constexpr double start(int d) { return d == 0 ? -0.5 : 0.0; }
     __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
+    template <bool ROLLED = false>
     __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double a = (double)(action - 1);                                        // ALL_ACTIONS = [-1, 0, 1]
         const double dv = dadd(dmul(0.001, a), dmul(-0.0025, cos(dmul(3.0, s[0]))));  // :58
@@ -101,9 +102,30 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
     }
 };
 
-// rsrl_domains/src/ode.rs:1-43 — k_i = f(...) * dx; y += (k1 + 2 k2 + 2 k3 + k4) / 6 in that association
-template <class Grad>
+// rsrl_domains/src/ode.rs:1-43 — k_i = f(...) * dx; y += (k1 + 2 k2 + 2 k3 + k4) / 6 in that association.
+// ROLLED = true keeps one copy of the gradient code (a 4-trip loop, same operations in the same order, bit-identical
+// results): used by kernels whose instruction footprint matters (f4tc.cuh).
+template <bool ROLLED = false, class Grad>
 __device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
+    if (ROLLED) {
+        double k[4], tmp[4], sum[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { tmp[i] = y[i]; sum[i] = 0.0; }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            f(tmp, k);
+            const bool mid = st == 1 || st == 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                k[i] = dmul(k[i], dx);
+                sum[i] = st == 0 ? k[i] : dadd(sum[i], mid ? dmul(2.0, k[i]) : k[i]);
+                tmp[i] = dadd(y[i], st < 2 ? ddiv(k[i], 2.0) : k[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = dadd(y[i], ddiv(sum[i], 6.0));
+        return;
+    }
     double k1[4], k2[4], k3[4], k4[4], tmp[4];
     f(y, k1);
 #pragma unroll
@@ -133,6 +155,7 @@ template <> struct Domain<RSRL_CART_POLE> {
     __device__ __forceinline__ static bool is_terminal(const double* s) {  // :83-97
         return s[0] <= -2.4 || s[0] >= 2.4 || s[2] <= -TWELVE_DEGREES || s[2] >= TWELVE_DEGREES;
     }
+    template <bool ROLLED = false>
     __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double force = action == 0 ? -10.0 : 10.0;  // ALL_ACTIONS :26
         constexpr double POLE_MOMENT = 0.5 * 0.1, TOTAL_MASS = 1.0 + 0.1, FOUR_THIRDS = 4.0 / 3.0, G = 9.8;
@@ -149,7 +172,7 @@ template <> struct Domain<RSRL_CART_POLE> {
             out[1] = dsub(z, dmul(dmul(0.5, out[3]), cos_t));
         };
         double ns[4] = {s[0], s[1], s[2], s[3]};
-        runge_kutta4(grad, ns, 0.02);
+        runge_kutta4<ROLLED>(grad, ns, 0.02);
         s[0] = dclip(-2.4, ns[0], 2.4);  // :44-49
         s[1] = dclip(-6.0, ns[1], 6.0);
         s[2] = dclip(-TWELVE_DEGREES, ns[2], TWELVE_DEGREES);
@@ -168,6 +191,7 @@ template <> struct Domain<RSRL_ACROBOT> {
     __device__ __forceinline__ static bool is_terminal(const double* s) {  // :56-58
         return dadd(cos(s[0]), cos(dadd(s[0], s[1]))) < -1.0;
     }
+    template <bool ROLLED = false>
     __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double torque = (double)(action - 1);  // ALL_ACTIONS = [-1, 0, 1] :36
         constexpr double G = 9.8, PI_OVER_2 = RSRL_PI / 2.0;
@@ -195,7 +219,7 @@ template <> struct Domain<RSRL_ACROBOT> {
             out[3] = ddiv(-dadd(dmul(d2, out[2]), phi1), d1);
         };
         double ns[4] = {s[0], s[1], s[2], s[3]};
-        runge_kutta4(grad, ns, 0.2);
+        runge_kutta4<ROLLED>(grad, ns, 0.2);
         s[0] = dwrap(-RSRL_PI, ns[0], RSRL_PI);  // :64-78
         s[1] = dwrap(-RSRL_PI, ns[1], RSRL_PI);
         s[2] = dclip(-4.0 * RSRL_PI, ns[2], 4.0 * RSRL_PI);

@@ -63,6 +63,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // non-blocking poll
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
 // Bounded wait: a tensor-pipe completion that never arrives raises the engine's fault flag instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fault) {
     for (int i = 0; i < (1 << 24); ++i)
@@ -141,21 +153,28 @@ __device__ __forceinline__ void f4tc_e(const float (&tcs)[4][7], const float (&t
     im = c == 0 ? 0.0f : tsn[d][c - 1];
 }
 // ---------------------------------------------------------------------------------------------------------------
-// env kernel: Q(s_t), behaviour action, Domain::step, Q(s'), TD error -> coef / from_states / actions for the dW pass.
-// CTA = 256 threads = two independent groups of 128; a group owns one tile of 128 envs at a time (thread = env = GEMM
-// row = TMEM lane), its own 32 KB operand buffer, 192 TMEM columns and one mbarrier; both groups share the W operand.
-// While one group generates operands / contracts its accumulator on the CUDA cores the other group's MMAs run.
+// One batched step = three kernels + the dW pass:
+//   f4tc_q_kernel<PHASE 0>  Q(s_t; W_t) for every env (tensor cores), tables of s_t for the dW pass
+//   f4tc_phys_kernel        behaviour action, Q(s_t)[a_t], Domain::step (f64 RK4) at full occupancy
+//   f4tc_q_kernel<PHASE 1>  Q(s'; W_t) (tensor cores), TD error -> coef, episode bookkeeping
+// (The f64 physics used to sit between the two evaluations inside one kernel: 30 % of that kernel's time at 8 warps/SM
+// with the tensor pipe idle; on its own it runs at 64 warps/SM.)
+// f4tc_q_kernel: CTA = 288 threads = two independent groups of 128 + one MMA-issuer warp; a group owns one tile of
+// 128 envs at a time (thread = env = GEMM row = TMEM lane), its own 32 KB operand buffer, 192 TMEM columns and a
+// full / done mbarrier pair; both groups share the W operand.  A group never blocks on MMA issue: it publishes a unit
+// (arrive on `full`), the issuer thread queues the unit's 12 MMAs and commits them to `done`.  While one group generates
+// operands / contracts its accumulator on the CUDA cores the other group's MMAs run.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW>
 struct F4tcEnvSmem {
     static constexpr int NB = AW * 64;                 // GEMM N: (a, i = (i0,i1))
     static constexpr int B_FLOATS = NB * 64;           // one of {hi, lo}
-    static constexpr int UNIT_FLOATS = 128 * 32;       // A unit: 128 rows x 32 k, one of {hi, lo}
-    static constexpr size_t bytes = (size_t)(2 * B_FLOATS + 4 * UNIT_FLOATS) * sizeof(float);
+    static constexpr int UNIT_FLOATS = 128 * 16;       // A unit: 128 rows x 16 k (a quarter of K), one of {hi, lo}
+    static constexpr size_t bytes = (size_t)(2 * B_FLOATS + 8 * UNIT_FLOATS) * sizeof(float);  // 2 groups x 2 buffers x {hi, lo}
 };
 
-template <int DOM, bool EXT>
-__global__ void __launch_bounds__(256, 1) f4tc_env_kernel(const StepArgs a, const F4Args fa, int n_tiles) {
+template <int DOM, int PHASE, bool EXT>
+__global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const F4Args fa, int n_tiles, int stagger, unsigned idle_ns) {
     using Dom = Domain<DOM>;
     constexpr int D = 4, P = 7, AW = Dom::A;
     using SM = F4tcEnvSmem<AW>;
@@ -168,18 +187,20 @@ __global__ void __launch_bounds__(256, 1) f4tc_env_kernel(const StepArgs a, cons
     extern __shared__ __align__(128) unsigned char f4tc_smem[];
     float* Bhi = reinterpret_cast<float*>(f4tc_smem);
     float* Blo = Bhi + SM::B_FLOATS;
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[2][2];   // done[g][b]: the MMAs of the unit in buffer b of group g completed
+    __shared__ __align__(8) unsigned long long fulls[2][2];  // full[g][b]: all 128 threads of group g stored their rows of buffer b
     __shared__ uint32_t tmem_slot;
 
-    const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, gwarp = gt >> 5;
-    float* Ahi = Blo + SM::B_FLOATS + grp * 2 * SM::UNIT_FLOATS;
-    float* Alo = Ahi + SM::UNIT_FLOATS;
+    const int tid = threadIdx.x, grp = (tid >> 7) & 1, gt = tid & 127, gwarp = gt >> 5;
+    const bool issuer_warp = tid >= 256;
+    float* Abase = Blo + SM::B_FLOATS;                        // [group][buffer][{hi, lo}][UNIT_FLOATS]
+    float* Agrp = Abase + grp * 4 * SM::UNIT_FLOATS;
     int* fault = &a.counters->pad;
 
     // ---- one-time setup: W -> B operand (row n = a*64 + i, column j), TMEM, barriers ----
     {
         const float* Wg = static_cast<const float*>(a.W);
-        for (int idx = tid; idx < 4096 * AW; idx += 256) {
+        for (int idx = tid; idx < 4096 * AW; idx += 288) {
             const int k = idx / AW, c = idx - k * AW;
             const int i = k >> 6, j = k & 63, n = c * 64 + i;
             float hi, lo;
@@ -191,161 +212,238 @@ __global__ void __launch_bounds__(256, 1) f4tc_env_kernel(const StepArgs a, cons
     }
     if (tid < 32) tc::tmem_alloc<TMEM_COLS>(&tmem_slot);
     if (tid == 0) {
-        tc::mbar_init(tc::smem_u32(&bars[0]), 1);
-        tc::mbar_init(tc::smem_u32(&bars[1]), 1);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            tc::mbar_init(tc::smem_u32(&bars[x >> 1][x & 1]), 1);
+            tc::mbar_init(tc::smem_u32(&fulls[x >> 1][x & 1]), 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+
+    if (issuer_warp) {
+        // ---- MMA issuer: serves whichever group has published a unit (units of a group alternate between its two buffers);
+        //      3xTF32 = hi*hi + lo*hi + hi*lo over the unit's 2 K steps ----
+        if (tid == 256) {
+            int units[2], cnt[2] = {0, 0};
+            uint32_t phf[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+                const int first = blockIdx.x * 2 + g2;
+                units[g2] = first < n_tiles ? ((n_tiles - first - 1) / ((int)gridDim.x * 2) + 1) * 8 : 0;  // 2 parts x 4 K quarters per tile
+            }
+            int spins = 0;
+            long long t_issue = 0, t_idle = 0, t_last = clock64();
+            while (cnt[0] < units[0] || cnt[1] < units[1]) {
+                bool progressed = false;
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    const int b = cnt[g2] & 1;
+                    if (cnt[g2] < units[g2] && tc::mbar_test_wait(tc::smem_u32(&fulls[g2][b]), b ? phf[g2][1] : phf[g2][0])) {
+                        if (b) phf[g2][1] ^= 1; else phf[g2][0] ^= 1;
+                        { const long long now = clock64(); t_idle += now - t_last; t_last = now; }
+                        tc::fence_after_sync();
+                        const int kq = cnt[g2] & 3;
+                        const float* Ah = Abase + (g2 * 4 + b * 2) * SM::UNIT_FLOATS;
+                        const float* Al = Ah + SM::UNIT_FLOATS;
+                        const uint32_t acc2 = tmem_slot + (uint32_t)(g2 * 256);
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t abase = tc::smem_u32(pass == 1 ? Al : Ah);
+                            const uint32_t bbase = tc::smem_u32(pass == 2 ? Blo : Bhi) + (uint32_t)kq * 4u * B_LBO;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks)
+                                tc::umma_tf32(acc2, tc::make_desc(abase + ks * 2 * A_LBO, A_LBO, SBO), tc::make_desc(bbase + ks * 2 * B_LBO, B_LBO, SBO),
+                                              IDESC, (kq | pass | ks) != 0 ? 1u : 0u);
+                        }
+                        tc::umma_commit(tc::smem_u32(&bars[g2][b]));
+                        { const long long now = clock64(); t_issue += now - t_last; t_last = now; }
+                        cnt[g2] += 1;
+                        progressed = true;
+                        spins = 0;
+                    }
+                }
+                if (!progressed) {
+                    __nanosleep(idle_ns);  // the poll loop shares a scheduler with two group warps: do not steal their issue slots
+                    if (++spins > (1 << 24)) { atomicExch(fault, 1); break; }
+                }
+            }
+            if (a.phase_prof) {  // issuer view: cycles blocked in MMA issue (queue full = tensor pipe busy) / waiting for a unit
+                a.phase_prof[(size_t)blockIdx.x * 8 + 6] += t_issue;
+                a.phase_prof[(size_t)blockIdx.x * 8 + 7] += t_idle;
+            }
+        }
+    } else {
     const uint32_t acc = tmem_slot + (uint32_t)(grp * 256);
     const uint32_t acc_lane = acc + ((uint32_t)(gwarp * 32) << 16);
-    const uint32_t bar = tc::smem_u32(&bars[grp]);
-    uint32_t ph = 0;  // phase parity of the group's barrier (uniform over the group)
+    const uint32_t bar0 = tc::smem_u32(&bars[grp][0]), bar1 = tc::smem_u32(&bars[grp][1]);
+    const uint32_t full0 = tc::smem_u32(&fulls[grp][0]), full1 = tc::smem_u32(&fulls[grp][1]);
+    uint32_t ph0 = 0, ph1 = 0;   // phase parity of the group's done barriers (uniform over the group)
+    int pend0 = 0, pend1 = 0;    // units published into buffer b whose completion has not been waited for yet (0 or 1)  // phase parity of the group's barrier (uniform over the group)
     const int a_row = (gt >> 3) * 32 + (gt & 7) * 4;  // float offset of the thread's row inside a 16-byte K chunk column
 
     float tcs[4][P], tsn[4][P];  // tables of the state being evaluated
+    // optional phase profile (RSRL_B200_PHASE_PROFILE=1): cycles of thread 0 per phase, summed over its tiles
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool profiling = a.phase_prof != nullptr && tid == 0;
+    long long tprev = profiling ? clock64() : 0;
+    auto mark = [&](int phase) {
+        if (profiling) { const long long now = clock64(); prof[phase] += now - tprev; tprev = now; }
+    };
 
-    // unit (part, kh): values of row gt, k = (i2 - 4 kh) * 8 + i3
-    auto unit_compute = [&](int part, int kh, float (&hi)[32], float (&lo)[32]) {
+    // Q of the state whose tables are in tcs/tsn; every thread of the group must call.  Rolled loops over the four operand
+    // units (part, kh) keep a single copy of every phase in the instruction stream: unit (part, 1) is generated while the
+    // MMAs of unit (part, 0) run; the accumulator is contracted with u after each part (real, then imaginary).
+    auto qeval = [&](float* q) {
 #pragma unroll
-        for (int i2l = 0; i2l < 4; ++i2l) {
-            float e2r, e2i;
-            f4tc_e(tcs, tsn, 2, P - (kh * 4 + i2l), e2r, e2i);
+        for (int c = 0; c < AW; ++c) q[c] = 0.0f;
+        auto unit_compute = [&](int part, int kq, float (&hi)[16], float (&lo)[16]) {
+            // v = e2[c2] * e3[c3]: real part e2r*e3r - e2i*e3i, imaginary part e2r*e3i + e2i*e3r = e2r*P + e2i*Q
+            float Pv[8], Qv[8];
 #pragma unroll
             for (int i3 = 0; i3 < 8; ++i3) {
                 float e3r, e3i;
                 f4tc_e(tcs, tsn, 3, P - i3, e3r, e3i);
-                const float v = part == 0 ? fmaf(e2r, e3r, -(e2i * e3i)) : fmaf(e2r, e3i, e2i * e3r);
-                tc::split(v, hi[i2l * 8 + i3], lo[i2l * 8 + i3]);
+                Pv[i3] = part ? e3i : e3r;
+                Qv[i3] = part ? e3r : -e3i;
             }
-        }
-    };
-    auto unit_store = [&](const float (&hi)[32], const float (&lo)[32]) {
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-            const int o = kc * (A_LBO / 4) + a_row;
-            *reinterpret_cast<float4*>(Ahi + o) = make_float4(hi[kc * 4], hi[kc * 4 + 1], hi[kc * 4 + 2], hi[kc * 4 + 3]);
-            *reinterpret_cast<float4*>(Alo + o) = make_float4(lo[kc * 4], lo[kc * 4 + 1], lo[kc * 4 + 2], lo[kc * 4 + 3]);
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        tc::group_sync(1 + grp, 128);
-    };
-    auto unit_issue = [&](int kh) {  // 3xTF32: hi*hi + lo*hi + hi*lo over the unit's 4 K steps
-        if (gt == 0) {
+            for (int i2l = 0; i2l < 2; ++i2l) {  // i2 = 2 kq + i2l, c2 = 7 - i2: warp-uniform select among the four quarters
+                float e2r, e2i, t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i;
+                f4tc_e(tcs, tsn, 2, P - i2l, t0r, t0i);
+                f4tc_e(tcs, tsn, 2, P - 2 - i2l, t1r, t1i);
+                f4tc_e(tcs, tsn, 2, P - 4 - i2l, t2r, t2i);
+                f4tc_e(tcs, tsn, 2, P - 6 - i2l, t3r, t3i);
+                e2r = kq == 0 ? t0r : kq == 1 ? t1r : kq == 2 ? t2r : t3r;
+                e2i = kq == 0 ? t0i : kq == 1 ? t1i : kq == 2 ? t2i : t3i;
+#pragma unroll
+                for (int i3 = 0; i3 < 8; ++i3) tc::split(fmaf(e2r, Pv[i3], e2i * Qv[i3]), hi[i2l * 8 + i3], lo[i2l * 8 + i3]);
+            }
+        };
+        auto wait_buf = [&](int b) {  // the MMAs of the last unit published into buffer b completed (no-op if already waited)
+            if (b == 0) { if (pend0) { tc::mbar_wait(bar0, ph0, fault); ph0 ^= 1; pend0 = 0; } }
+            else { if (pend1) { tc::mbar_wait(bar1, ph1, fault); ph1 ^= 1; pend1 = 0; } }
+        };
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll 1
+            for (int kq = 0; kq < 4; ++kq) {
+                const int b = kq & 1;
+                float hi[16], lo[16];
+                unit_compute(part, kq, hi, lo);  // overlaps the MMAs of the previous units
+                mark(1);
+                wait_buf(b);                     // buffer b free again
+                mark(2);
+                float* Ahi = Agrp + b * 2 * SM::UNIT_FLOATS;
+                float* Alo = Ahi + SM::UNIT_FLOATS;
+#pragma unroll
+                for (int kc = 0; kc < 4; ++kc) {
+                    const int o = kc * (A_LBO / 4) + a_row;
+                    *reinterpret_cast<float4*>(Ahi + o) = make_float4(hi[kc * 4], hi[kc * 4 + 1], hi[kc * 4 + 2], hi[kc * 4 + 3]);
+                    *reinterpret_cast<float4*>(Alo + o) = make_float4(lo[kc * 4], lo[kc * 4 + 1], lo[kc * 4 + 2], lo[kc * 4 + 3]);
+                }
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                tc::mbar_arrive(b ? full1 : full0);  // publish the unit: the issuer warp queues its MMAs and commits them to done[b]
+                if (b) pend1 = 1; else pend0 = 1;
+                mark(4);
+            }
+            wait_buf(0);
+            wait_buf(1);  // all four units of this part done: accumulator complete
+            mark(2);
+            {
+            // q_a += sum_i uu_i P[a*64 + i], uu = Re(e0 e1) (real part) or -Im(e0 e1) (imaginary part) = e0r*Pu + e0i*Qu
+            const int cpart = part;
+            __syncwarp();  // tcgen05.ld is .sync.aligned: the issuing thread rejoins its warp
             tc::fence_after_sync();
+            float Pu[8], Qu[8];
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t abase = tc::smem_u32(pass == 1 ? Alo : Ahi);
-                const uint32_t bbase = tc::smem_u32(pass == 2 ? Blo : Bhi) + (uint32_t)kh * 8u * B_LBO;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    tc::umma_tf32(acc, tc::make_desc(abase + ks * 2 * A_LBO, A_LBO, SBO), tc::make_desc(bbase + ks * 2 * B_LBO, B_LBO, SBO), IDESC,
-                                  (kh | pass | ks) != 0 ? 1u : 0u);
+            for (int i1 = 0; i1 < 8; ++i1) {
+                float e1r, e1i;
+                f4tc_e(tcs, tsn, 1, P - i1, e1r, e1i);
+                Pu[i1] = cpart ? -e1i : e1r;
+                Qu[i1] = cpart ? -e1r : -e1i;
             }
-            tc::umma_commit(bar);
-        }
-    };
-    auto unit_wait = [&]() { tc::mbar_wait(bar, ph, fault); ph ^= 1; };
-    // q_a += sum_i u_i P[a*64 + i]: u = Re(e0 e1) for the real part, -Im(e0 e1) for the imaginary part
-    auto contract = [&](int part, float* q) {
-        __syncwarp();  // tcgen05.ld is .sync.aligned: the issuing thread rejoins its warp
-        tc::fence_after_sync();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t r[AW][32];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[2][32];  // two TMEM load buffers: the load of action c+1 is in flight during the FMAs of action c
+                tc::tmem_ld32_issue(acc_lane + (uint32_t)(h * 32), r[0]);
+                float uu[32];
 #pragma unroll
-            for (int c = 0; c < AW; ++c) tc::tmem_ld32_issue(acc_lane + (uint32_t)(c * 64 + h * 32), r[c]);
-            float uu[32];
+                for (int i0l = 0; i0l < 4; ++i0l) {
+                    float e0r, e0i;
+                    f4tc_e(tcs, tsn, 0, P - (h * 4 + i0l), e0r, e0i);
 #pragma unroll
-            for (int i0l = 0; i0l < 4; ++i0l) {
-                float e0r, e0i;
-                f4tc_e(tcs, tsn, 0, P - (h * 4 + i0l), e0r, e0i);
+                    for (int i1 = 0; i1 < 8; ++i1) uu[i0l * 8 + i1] = fmaf(e0r, Pu[i1], e0i * Qu[i1]);
+                }
 #pragma unroll
-                for (int i1 = 0; i1 < 8; ++i1) {
-                    float e1r, e1i;
-                    f4tc_e(tcs, tsn, 1, P - i1, e1r, e1i);
-                    uu[i0l * 8 + i1] = part == 0 ? fmaf(e0r, e1r, -(e0i * e1i)) : -fmaf(e0r, e1i, e0i * e1r);
+                for (int c = 0; c < AW; ++c) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld_fence(r[c & 1]);
+                    if (c + 1 < AW) tc::tmem_ld32_issue(acc_lane + (uint32_t)((c + 1) * 64 + h * 32), r[(c + 1) & 1]);
+                    float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;  // four chains per action
+#pragma unroll
+                    for (int x = 0; x < 32; x += 4) {
+                        q0 = fmaf(uu[x], __uint_as_float(r[c & 1][x]), q0);
+                        q1 = fmaf(uu[x + 1], __uint_as_float(r[c & 1][x + 1]), q1);
+                        q2 = fmaf(uu[x + 2], __uint_as_float(r[c & 1][x + 2]), q2);
+                        q3 = fmaf(uu[x + 3], __uint_as_float(r[c & 1][x + 3]), q3);
+                    }
+                    q[c] += (q0 + q1) + (q2 + q3);
                 }
             }
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < AW; ++c) {
-                tc::tmem_ld_fence(r[c]);
-#pragma unroll
-                for (int x = 0; x < 32; ++x) q[c] = fmaf(uu[x], __uint_as_float(r[c][x]), q[c]);
+            tc::fence_before_sync();  // orders these TMEM reads before the next MMAs into the accumulator
             }
+            mark(3);
         }
-        tc::fence_before_sync();  // orders these TMEM reads before the next unit_issue (after its group_sync)
-    };
-    // Q of the state whose tables are in tcs/tsn; every thread of the group must call
-    auto qeval = [&](float* q) {
-        float hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < AW; ++c) q[c] = 0.0f;
-        unit_compute(0, 0, hi, lo);
-        unit_store(hi, lo);
-        unit_issue(0);
-        unit_compute(0, 1, hi, lo);
-        unit_wait();
-        unit_store(hi, lo);
-        unit_issue(1);
-        unit_compute(1, 0, hi, lo);
-        unit_wait();
-        contract(0, q);
-        unit_store(hi, lo);
-        unit_issue(0);
-        unit_compute(1, 1, hi, lo);
-        unit_wait();
-        unit_store(hi, lo);
-        unit_issue(1);
-        unit_wait();
-        contract(1, q);
     };
 
+    // The two groups run identical work: started together they drain the tensor pipe at the same moments (both
+    // contracting, both building tables) and it idles half of the time.  Group 1 starts half a part late.
+    if (grp == 1 && stagger > 0) { const long long t0 = clock64(); while (clock64() - t0 < stagger) {} }
+    (void)idle_ns;
     for (int tile = blockIdx.x * 2 + grp; tile < n_tiles; tile += gridDim.x * 2) {
         const int64_t i = (int64_t)tile * 128 + gt;
         const bool active = i < a.n;
         const uint64_t g = (uint64_t)(a.env_offset + (active ? i : 0));
         double s[D];
+        const double* src = PHASE == 0 ? (EXT ? a.ext_from : a.states) : fa.next_states;
 #pragma unroll
-        for (int d = 0; d < D; ++d) s[d] = active ? (EXT ? a.ext_from[i * D + d] : a.states[i * D + d]) : Dom::start(d);
-        if (active) {
+        for (int d = 0; d < D; ++d) s[d] = active ? src[i * D + d] : Dom::start(d);
+        f4_tables<float, Dom, P, RSRL_FOURIER>(s, tcs, tsn);
+        if (PHASE == 0 && active) {  // tables of s_t for the dW pass: [d][c-1][{cos, sin}][env], env fastest (coalesced)
+            float* tb = fa.tabs + i;
 #pragma unroll
-            for (int d = 0; d < D; ++d) fa.from_states[i * D + d] = s[d];
-        }
-        bool nonfinite = false, terminated = false;
-        int act = 0;
-        float qsa = 0.0f, residual = 0.0f;
-        double reward = 0.0;
-#pragma unroll 1
-        for (int ev = 0; ev < 2; ++ev) {
-            f4_tables<float, Dom, P, RSRL_FOURIER>(s, tcs, tsn);
-            float q[AW];
-            qeval(q);
-            if (ev == 0) {
-                // ---- B: behaviour action and Q(s_t, a_t) under W_t (kernels.cuh:env_core) ----
-                if (EXT) act = active ? a.ext_actions[i] : 0;
-                else act = policy_sample<float, AW>(a.pol, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
-                qsa = q[0];
+            for (int d = 0; d < D; ++d)
 #pragma unroll
-                for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
-                // ---- C: Domain::transition ----
-                if (EXT) {
-                    if (active) {
-#pragma unroll
-                        for (int d = 0; d < D; ++d) s[d] = a.ext_to[i * D + d];
-                        reward = a.ext_rewards[i];
-                        terminated = a.ext_term[i] != 0;
-                    }
-                } else {
-                    Dom::step(s, act, reward, terminated);
+                for (int j = 0; j < P; ++j) {
+                    tb[(size_t)((d * P + j) * 2) * a.n] = tcs[d][j];
+                    tb[(size_t)((d * P + j) * 2 + 1) * a.n] = tsn[d][j];
                 }
-            } else if (terminated) {
-                // ---- D: TD error with W_t (Q(s') is evaluated for every row; terminal rows ignore it) ----
-                residual = (float)reward - qsa;
+        }
+        float q[AW];
+        mark(0);
+        qeval(q);
+        if (PHASE == 0) {
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < AW; ++c) fa.q[i * 4 + c] = q[c];
+            }
+            mark(5);
+            continue;
+        }
+        if (active) {
+            // ---- D: TD error with W_t (kernels.cuh:env_core); Q(s') was evaluated for every row, terminal rows ignore it ----
+            const float4 aux = reinterpret_cast<const float4*>(fa.aux)[i];   // {Q(s_t)[a_t], reward, terminal, -} from the physics kernel
+            const float qsa = aux.x, reward = aux.y;
+            const bool terminated = aux.z != 0.0f;
+            bool nonfinite = false;
+            float residual;
+            if (terminated) {
+                residual = reward - qsa;
             } else {
                 float target;
                 if (a.algo == RSRL_QLEARNING || a.algo == RSRL_Q_LAMBDA) {
@@ -362,27 +460,65 @@ __global__ void __launch_bounds__(256, 1) f4tc_env_kernel(const StepArgs a, cons
 #pragma unroll
                     for (int c = 0; c < AW; ++c) target = target + q[c] * p[c];
                 }
-                residual = (float)reward + (float)a.gamma * target - qsa;
+                residual = reward + (float)a.gamma * target - qsa;
             }
-        }
-        const float coef = a.algo == RSRL_EXPECTED_SARSA ? (float)a.lr_scaled * ((float)a.alpha * residual) : (float)a.lr_scaled * residual;
-
-        if (active) {
+            const float coef = a.algo == RSRL_EXPECTED_SARSA ? (float)a.lr_scaled * ((float)a.alpha * residual) : (float)a.lr_scaled * residual;
             if (a.td) static_cast<float*>(a.td)[i] = residual;
             if (nonfinite) atomicExch(&a.counters->nonfinite, 1);
             static_cast<float*>(fa.coef)[i] = coef;
-            a.actions[i] = act;
             if (!EXT) {
                 a.ep_steps[i] = env_bookkeeping<Dom>(a, a.t, i, g, s, a.ep_steps[i], terminated);
 #pragma unroll
                 for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
             }
         }
+        mark(5);
     }
 
+    if (profiling) {
+#pragma unroll
+        for (int x = 0; x < 6; ++x) a.phase_prof[(size_t)blockIdx.x * 8 + x] += prof[x];
+    }
+    }  // group threads
     tc::fence_before_sync();
     __syncthreads();
     if (tid < 32) tc::tmem_free<TMEM_COLS>(tmem_slot);
+}
+
+// behaviour action + Domain::transition for every env (phases B and C of kernels.cuh:env_core), one thread per env
+template <int DOM, bool EXT>
+__global__ void __launch_bounds__(128) f4tc_phys_kernel(const StepArgs a, const F4Args fa) {
+    using Dom = Domain<DOM>;
+    constexpr int D = 4, AW = Dom::A;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t g = (uint64_t)(a.env_offset + i);
+    float q[AW];
+#pragma unroll
+    for (int c = 0; c < AW; ++c) q[c] = fa.q[i * 4 + c];
+    bool nonfinite = false, terminated;
+    int act;
+    double reward, s[D];
+    if (EXT) {
+        act = a.ext_actions[i];
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = a.ext_to[i * D + d];
+        reward = a.ext_rewards[i];
+        terminated = a.ext_term[i] != 0;
+    } else {
+        act = policy_sample<float, AW>(a.pol, q, g, a.t, STREAM_BEHAVIOUR, nonfinite);
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = a.states[i * D + d];
+        Dom::step(s, act, reward, terminated);
+    }
+    float qsa = q[0];
+#pragma unroll
+    for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
+#pragma unroll
+    for (int d = 0; d < D; ++d) fa.next_states[i * D + d] = s[d];
+    reinterpret_cast<float4*>(fa.aux)[i] = make_float4(qsa, (float)reward, terminated ? 1.0f : 0.0f, 0.0f);
+    a.actions[i] = act;  // (EXT: the caller's action, consumed by the dW pass)
+    if (nonfinite) atomicExch(&a.counters->nonfinite, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -400,13 +536,13 @@ struct F4tcDwSmem {
     static constexpr int A_FLOATS = 8 * A_LBO / 4;          // one of {hi, lo}: 8 K chunks (32 envs)
     static constexpr int B_FLOATS = 8 * B_LBO / 4;
     static constexpr int UNIT_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
-    static constexpr int TAB_FLOATS = 4 * 7 * 2 * 32;       // [d][c-1][{cos,sin}][env lane]
-    static constexpr size_t bytes = (size_t)(2 * UNIT_FLOATS + TAB_FLOATS + 2 * 32) * sizeof(float);
+    static constexpr size_t bytes = (size_t)(2 * UNIT_FLOATS) * sizeof(float);
 };
 
 template <int DOM>
-__global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double* __restrict__ from_states, const float* __restrict__ coef,
-                                                         const int32_t* __restrict__ actions, float* __restrict__ partials, Counters* counters) {
+__global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float* __restrict__ tabs_g, const float* __restrict__ coef,
+                                                         const int32_t* __restrict__ actions, float* __restrict__ partials, Counters* counters,
+                                                         long long* phase_prof) {
     using Dom = Domain<DOM>;
     constexpr int P = 7, AW = Dom::A;
     using SM = F4tcDwSmem<AW>;
@@ -417,9 +553,6 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double
 
     extern __shared__ __align__(128) unsigned char f4tc_smem[];
     float* units = reinterpret_cast<float*>(f4tc_smem);
-    float* tabs = units + 2 * SM::UNIT_FLOATS;
-    float* dco = tabs + SM::TAB_FLOATS;                    // [32] coef
-    int* dact = reinterpret_cast<int*>(dco + 32);          // [32] action (-1: padding env)
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t tmem_slot;
 
@@ -448,65 +581,55 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double
     const int m0 = qi * 16 + hq * 8;  // rows m0 .. m0+7 = (i1 = 4 hq + r/2, b = r%2): one 8-row group
     const int oa = ka + (m0 >> 3) * 32;
 
-    for (int64_t st = s_begin; st < s_end; ++st) {
+    // Inputs of one sub-tile for this thread: the table entries e_d[c] of env `lane` it needs (written by the env kernel,
+    // [d][c-1][{cos,sin}][env], env fastest => coalesced), the scaled TD error and the action.  Loaded one sub-tile ahead.
+    struct In { float e0r, e0i, e24r, e24i, e3r, e3i, e1r[4], e1i[4], e2r[2], e2i[2], dc; int act; };
+    auto load_in = [&](int64_t st, In& in) {
         const int64_t env = st * 32 + lane;
-        // ---- per-env tables: warp d < 4 builds dimension d of env `lane` ----
-        if (q < 4) {
-            float c1 = 1.0f, s1 = 0.0f;
-            if (env < n) {
-                const double x = from_states[env * 4 + q];
-                const double lo = Dom::lo(q), hi = Dom::hi(q);
-                const float xh = (float)dmul(dsub(x, lo), 1.0 / (hi - lo));  // == grid_prepare (f32)
-                sincospif(xh, &s1, &c1);
-            }
-            float cj = c1, sj = s1;
-            float* t = tabs + (q * 7) * 64 + lane;
-            t[0] = cj; t[32] = sj;
-#pragma unroll
-            for (int j = 1; j < P; ++j) {
-                const float cn = fmaf(cj, c1, -(sj * s1)), sn = fmaf(sj, c1, cj * s1);
-                cj = cn; sj = sn;
-                t[j * 64] = cj; t[j * 64 + 32] = sj;
-            }
-        } else if (q == 4) {
-            dco[lane] = env < n ? coef[env] : 0.0f;
-            dact[lane] = env < n ? actions[env] : -1;
-        }
-        __syncthreads();
-        auto E = [&](int d, int c, float& re, float& im) {  // e_d[c] of env `lane`
-            re = c == 0 ? 1.0f : tabs[(d * 7 + c - 1) * 64 + lane];
-            im = c == 0 ? 0.0f : tabs[(d * 7 + c - 1) * 64 + 32 + lane];
+        const bool ok = st < s_end && env < n;
+        auto E = [&](int d, int c, float& re, float& im) {
+            re = c == 0 ? 1.0f : (ok ? tabs_g[(size_t)((d * 7 + c - 1) * 2) * n + env] : 0.0f);
+            im = c == 0 ? 0.0f : (ok ? tabs_g[(size_t)((d * 7 + c - 1) * 2 + 1) * n + env] : 0.0f);
         };
+        E(0, P - qi, in.e0r, in.e0i);
+        E(2, 4, in.e24r, in.e24i);
+        E(3, P - qi, in.e3r, in.e3i);
+#pragma unroll
+        for (int i1l = 0; i1l < 4; ++i1l) E(1, P - (hq * 4 + i1l), in.e1r[i1l], in.e1i[i1l]);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) E(2, 3 - (hq * 2 + x), in.e2r[x], in.e2i[x]);
+        in.dc = ok ? coef[env] : 0.0f;
+        in.act = ok ? actions[env] : -1;
+    };
+    In cur, nxt;
+    load_in(s_begin, cur);
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool profiling = phase_prof != nullptr && tid == 0;
+    long long tprev = profiling ? clock64() : 0;
+    auto mark = [&](int phase) {
+        if (profiling) { const long long now = clock64(); prof[phase] += now - tprev; tprev = now; }
+    };
+
+    for (int64_t st = s_begin; st < s_end; ++st) {
+        load_in(st + 1, nxt);
         // u_m = e0[7-i0] * e1[7-i1] * (b == 0 ? e2[4] : 1), rows r = (i1 - 4 hq)*2 + b
         float ur[8], ui[8];
-        {
-            float e0r, e0i, e24r, e24i;
-            E(0, P - qi, e0r, e0i);
-            E(2, 4, e24r, e24i);
 #pragma unroll
-            for (int i1l = 0; i1l < 4; ++i1l) {
-                float e1r, e1i;
-                E(1, P - (hq * 4 + i1l), e1r, e1i);
-                const float tr = fmaf(e0r, e1r, -(e0i * e1i)), ti = fmaf(e0r, e1i, e0i * e1r);
-                ur[i1l * 2 + 1] = tr; ui[i1l * 2 + 1] = ti;                                            // b = 1: c2 high part 0
-                ur[i1l * 2] = fmaf(tr, e24r, -(ti * e24i)); ui[i1l * 2] = fmaf(tr, e24i, ti * e24r);   // b = 0: times e2[4]
-            }
+        for (int i1l = 0; i1l < 4; ++i1l) {
+            const float tr = fmaf(cur.e0r, cur.e1r[i1l], -(cur.e0i * cur.e1i[i1l])), ti = fmaf(cur.e0r, cur.e1i[i1l], cur.e0i * cur.e1r[i1l]);
+            ur[i1l * 2 + 1] = tr; ui[i1l * 2 + 1] = ti;                                                            // b = 1: c2 high part 0
+            ur[i1l * 2] = fmaf(tr, cur.e24r, -(ti * cur.e24i)); ui[i1l * 2] = fmaf(tr, cur.e24i, ti * cur.e24r);   // b = 0: times e2[4]
         }
         // v_n' = e2[3-i2'] * e3[7-i3], i3 = qi, i2' = 2 hq + x
         float vr[2], vi[2];
-        {
-            float e3r, e3i;
-            E(3, P - qi, e3r, e3i);
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                float e2r, e2i;
-                E(2, 3 - (hq * 2 + x), e2r, e2i);
-                vr[x] = fmaf(e2r, e3r, -(e2i * e3i));
-                vi[x] = fmaf(e2r, e3i, e2i * e3r);
-            }
+        for (int x = 0; x < 2; ++x) {
+            vr[x] = fmaf(cur.e2r[x], cur.e3r, -(cur.e2i[x] * cur.e3i));
+            vi[x] = fmaf(cur.e2r[x], cur.e3i, cur.e2i[x] * cur.e3r);
         }
-        const float dc = dco[lane];
-        const int act = dact[lane];
+        const float dc = cur.dc;
+        const int act = cur.act;
+        mark(0);
 
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
@@ -516,6 +639,7 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double
             float* Blo = Bhi + SM::B_FLOATS;
             if (used[part]) { tc::mbar_wait(tc::smem_u32(&bars[part]), ph[part], fault); ph[part] ^= 1; }
             used[part] = true;
+            mark(1);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 float hi, lo;
@@ -534,9 +658,11 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double
                     Bhi[o] = hi;
                     Blo[o] = lo;
                 }
+            mark(2);
             tc::fence_async_smem();
             tc::fence_before_sync();
             __syncthreads();
+            mark(3);
             if (tid == 0) {
                 tc::fence_after_sync();
 #pragma unroll
@@ -551,8 +677,13 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const double
                 }
                 tc::umma_commit(tc::smem_u32(&bars[part]));
             }
+            mark(4);
         }
-        // the next sub-tile's table writes happen after the two __syncthreads above: every thread has read its tables
+        cur = nxt;
+    }
+    if (profiling) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) phase_prof[(size_t)blockIdx.x * 8 + x] += prof[x];
     }
 
     // ---- drain + epilogue: TMEM [m = i0*16 + i1*2 + b][n = a*32 + i2'*8 + i3] -> partials[cta][k*AW + a] ----

@@ -1,12 +1,13 @@
 // f4tc_inst.cu — instantiations + host launchers of the tcgen05 path (f4tc.cuh): order-7 Fourier, 4-D domains, f32
+#include <cstdlib>
 #include "f4tc_launch.h"
 #include "f4tc.cuh"
 
 namespace rsrl {
 
-template <int DOM, bool EXT>
-static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
-    auto kern = f4tc_env_kernel<DOM, EXT>;
+template <int DOM, int PHASE, bool EXT>
+static cudaError_t q_one(const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
+    auto kern = f4tc_q_kernel<DOM, PHASE, EXT>;
     constexpr size_t smem = F4tcEnvSmem<Domain<DOM>::A>::bytes;
     static bool configured = false;
     if (!configured) {
@@ -14,10 +15,22 @@ static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int n_tiles, int
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, 256, smem, st>>>(a, fa, n_tiles);
+    static const int stagger = getenv("RSRL_B200_F4TC_STAGGER") ? atoi(getenv("RSRL_B200_F4TC_STAGGER")) : 2500;  // cycles (tuning aid)
+    static const unsigned idle_ns = getenv("RSRL_B200_F4TC_IDLE_NS") ? (unsigned)atoi(getenv("RSRL_B200_F4TC_IDLE_NS")) : 50u;
+    kern<<<grid, 288, smem, st>>>(a, fa, n_tiles, stagger, idle_ns);
     return cudaGetLastError();
 }
 
+template <int DOM, bool EXT>
+static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
+    cudaError_t e = q_one<DOM, 0, EXT>(a, fa, n_tiles, grid, st);
+    if (e != cudaSuccess) return e;
+    f4tc_phys_kernel<DOM, EXT><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a, fa);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return q_one<DOM, 1, EXT>(a, fa, n_tiles, grid, st);
+}
+
+// Q(s_t) -> action + physics -> Q(s') + TD error: three launches
 cudaError_t launch_f4tc_env(int domain, bool ext, const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
     if (domain == RSRL_CART_POLE) return ext ? env_one<RSRL_CART_POLE, true>(a, fa, n_tiles, grid, st) : env_one<RSRL_CART_POLE, false>(a, fa, n_tiles, grid, st);
     if (domain == RSRL_ACROBOT) return ext ? env_one<RSRL_ACROBOT, true>(a, fa, n_tiles, grid, st) : env_one<RSRL_ACROBOT, false>(a, fa, n_tiles, grid, st);
@@ -25,8 +38,8 @@ cudaError_t launch_f4tc_env(int domain, bool ext, const StepArgs& a, const F4Arg
 }
 
 template <int DOM>
-static cudaError_t dw_one(int64_t n, const double* from_states, const void* coef, const int32_t* actions, int grid, void* partials,
-                          Counters* counters, cudaStream_t st) {
+static cudaError_t dw_one(int64_t n, const float* tabs, const void* coef, const int32_t* actions, int grid, void* partials,
+                          Counters* counters, long long* prof, cudaStream_t st) {
     auto kern = f4tc_dw_kernel<DOM>;
     constexpr size_t smem = F4tcDwSmem<Domain<DOM>::A>::bytes;
     static bool configured = false;
@@ -35,14 +48,14 @@ static cudaError_t dw_one(int64_t n, const double* from_states, const void* coef
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, 512, smem, st>>>(n, from_states, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters);
+    kern<<<grid, 512, smem, st>>>(n, tabs, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters, prof);
     return cudaGetLastError();
 }
 
-cudaError_t launch_f4tc_dw(int domain, int64_t n, const double* from_states, const void* coef, const int32_t* actions, int grid,
-                           void* partials, Counters* counters, cudaStream_t st) {
-    if (domain == RSRL_CART_POLE) return dw_one<RSRL_CART_POLE>(n, from_states, coef, actions, grid, partials, counters, st);
-    if (domain == RSRL_ACROBOT) return dw_one<RSRL_ACROBOT>(n, from_states, coef, actions, grid, partials, counters, st);
+cudaError_t launch_f4tc_dw(int domain, int64_t n, const float* tabs, const void* coef, const int32_t* actions, int grid,
+                           void* partials, Counters* counters, long long* prof, cudaStream_t st) {
+    if (domain == RSRL_CART_POLE) return dw_one<RSRL_CART_POLE>(n, tabs, coef, actions, grid, partials, counters, prof, st);
+    if (domain == RSRL_ACROBOT) return dw_one<RSRL_ACROBOT>(n, tabs, coef, actions, grid, partials, counters, prof, st);
     return cudaErrorInvalidDeviceFunction;
 }
 

@@ -39,6 +39,11 @@ __device__ __forceinline__ void cmul(R ar, R ai, R br, R bi, R& cr, R& ci) {
 struct F4Args {
     double* from_states;  // [N][4]  s_t saved for the dW pass
     void* coef;           // R[N]    scaled TD error
+    // f4tc.cuh only (else nullptr):
+    float* tabs;          // float[56][N] per-dimension sin/cos tables of s_t (env fastest)
+    float* q;             // float[N][4]  Q(s_t; W_t)
+    float* aux;           // float4[N]    {Q(s_t)[a_t], reward, terminal, -}
+    double* next_states;  // [N][4]       s' before the episode bookkeeping
 };
 
 // Outer-dimension tables live in shared memory as columns of the calling thread:

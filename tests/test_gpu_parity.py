@@ -588,6 +588,87 @@ def test_cfg4_shape_properties(E):
     assert outs[0][2]["total_steps"] == 16384 * 20 and outs[0][2]["nonfinite"] == 0
 
 
+# tcgen05 path (f4tc.cuh): order 7, dtype f32.  The GEMMs run as 3xTF32 tensor-core MMAs with fp32 accumulation; the bar is
+# the same fp32 tolerance as the CUDA-core f32 kernels (teacher-forced single steps against the oracle).
+def _f4tc_cfg(domain, n, algo, **kw):
+    base = dict(domain=domain, basis_order=7, algo=algo, policy=abi.EPSILON_GREEDY, epsilon=0.1, n_envs=n, dtype=abi.F32,
+                init_mode=abi.INIT_UNIFORM, init_lo=[-0.1] * 4, init_hi=[0.1] * 4, max_episode_steps=500, seed=5, gamma=0.99,
+                lr=1e-4, alpha=1.0, update_scale=abi.SCALE_MEAN, record_td_error=1)
+    base.update(kw)
+    return abi.default_config(**base)
+
+
+@pytest.mark.parametrize("domain,n,algo", [(AC, 300, abi.EXPECTED_SARSA), (CP, 1000, abi.QLEARNING), (AC, 4113, abi.SARSA)])
+def test_f4tc_single_step_matches_oracle(E, oracle, domain, n, algo):
+    """n is ragged on purpose (not a multiple of the 128-env GEMM tile or the 32-env dW sub-tile)."""
+    cfg = _f4tc_cfg(domain, n, algo)
+    A = oracle.domain_dims(domain)[1]
+    W0 = np.random.default_rng(1).normal(size=(4096, A)) * 0.05
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.set_weights(W0)
+        o.set_weights(W0)
+        e.step(1)
+        o.step(1)
+        e.sync()
+        assert e.stats()["kernel_launches"] >= 3
+        td_o = o.td_errors()
+        assert np.abs(e.td_errors() - td_o).max() < 1.2e-5 * max(1.0, np.abs(td_o).max())    # fp32 tolerance (3xTF32: ~5e-6 measured)
+        assert (e.actions() == o.actions()).all() and (e.episode_steps() == o.episode_steps()).all()
+        assert np.abs(e.states() - o.states()).max() < 1e-12                                # f64 physics
+        assert np.abs(e.weights() - o.weights()).max() < 1e-6 * np.abs(o.weights()).max()
+
+
+def test_f4tc_dw_from_zero_weights(E, oracle):
+    """W0 = 0 => Q = 0, TD error = reward: the weights after one step ARE dW = sum_env coef * phi(s_env) — checks the
+    Phi^T D tensor-core contraction alone, relative to the largest update."""
+    cfg = _f4tc_cfg(AC, 2500, abi.EXPECTED_SARSA, lr=0.05, update_scale=abi.SCALE_SUM)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(1)
+        o.step(1)
+        e.sync()
+        dW = o.weights()
+        assert np.abs(dW).max() > 1.0
+        assert np.abs(e.weights() - dW).max() < 2e-6 * np.abs(dW).max()
+
+
+def test_f4tc_free_run_matches_cuda_core_path(E, monkeypatch):
+    """Same engine config on the tensor-core path and on the CUDA-core f32 path (RSRL_B200_F4TC=0): 12 free-running
+    steps from W = 0; trajectories stay identical as long as no decision is closer than the fp32 noise of Q."""
+    cfg = _f4tc_cfg(AC, 1500, abi.EXPECTED_SARSA, lr=1e-3, seed=11)
+    outs = []
+    for mask in ("0", "3"):
+        monkeypatch.setenv("RSRL_B200_F4TC", mask)
+        with E.Engine(cfg) as e:
+            e.step(12)
+            e.sync()
+            outs.append((e.weights(), e.states(), e.actions(), e.stats()))
+    (W0, S0, A0, st0), (W1, S1, A1, st1) = outs
+    assert (A0 == A1).mean() > 0.99 and st0["total_steps"] == st1["total_steps"]
+    assert np.abs(W0 - W1).max() < 1e-5 * max(np.abs(W0).max(), 1e-6) + 1e-9
+    same = (A0 == A1)
+    assert np.abs(S0[same] - S1[same]).max() < 1e-6
+
+
+def test_f4tc_handle_entry_point(E, oracle):
+    cfg = _f4tc_cfg(AC, 700, abi.QLEARNING)
+    rng = np.random.default_rng(4)
+    lo, hi = oracle.domain_limits(AC)
+    s = rng.uniform(lo, hi, size=(700, 4)) * 0.3
+    a = rng.integers(0, 3, 700).astype(np.int32)
+    ns, r, term = oracle.domain_step(AC, s, a)
+    W0 = rng.normal(size=(4096, 3)) * 0.05
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.set_weights(W0)
+        o.set_weights(W0)
+        td_e, td_o = e.handle(s, a, r, ns, term, draw_idx=3), o.handle(s, a, r, ns, term, draw_idx=3)
+        assert np.abs(td_e - td_o).max() < 1.2e-5 * max(1.0, np.abs(td_o).max())
+        assert np.abs(e.weights() - o.weights()).max() < 1e-6 * np.abs(o.weights()).max()
+        assert np.abs(e.evaluate(s) - oracle.evaluate(cfg, o.weights(), s)).max() < 2e-5 * 10 * 64
+
+
 # ---------------------------------------------------------------------------------------------
 # C++ host-side mirror of the reference's trait surface (include/rsrl_b200.hpp): examples/q_learning.cpp is
 # rsrl/examples/q_learning.rs line by line; its episode lengths must equal the oracle's.

@@ -70,9 +70,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // canonical no-swizzle layouts, R rows (M or N) x K, 4-byte elements; byte offset of element (r, k)
-__host__ __device__ inline uint32_t off_kmajor(int R, int r, int k, bool swap) {
+__host__ __device__ inline uint32_t off_kmajor(int R, int r, int k, bool swap, int pad = 0) {
     const uint32_t mn_stride = swap ? (uint32_t)(64 / 4) * 128u : 128u;   // normal: row groups adjacent, K chunks far apart
-    const uint32_t k_stride = swap ? 128u : (uint32_t)(R / 8) * 128u;
+    const uint32_t k_stride = swap ? 128u : (uint32_t)(R / 8) * 128u + (uint32_t)pad;
     return (uint32_t)(k / 4) * k_stride + (uint32_t)(r / 8) * mn_stride + (uint32_t)(r % 8) * 16u + (uint32_t)(k % 4) * 4u;
 }
 __host__ __device__ inline uint32_t off_mnmajor(int R, int r, int k) {
@@ -83,7 +83,7 @@ struct Params {
     const float* A;  // [128][64]
     const float* B;  // [N][64]
     float* D;        // [128][N]
-    int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna;
+    int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad;
     long long* cycles;
     int* flags;
 };
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     constexpr int M = 128, K = 64;
     const int N = p.N;
     float* Ahi = reinterpret_cast<float*>(smem);
-    float* Alo = Ahi + M * K;
-    float* Bhi = Alo + M * K;
-    float* Blo = Bhi + N * K;
+    float* Alo = Ahi + M * K + 16 * 16;
+    float* Bhi = Alo + M * K + 16 * 16;
+    float* Blo = Bhi + N * K + 16 * 16;
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
         const int r = idx / K, k = idx % K;
         const float x = p.A[idx];
         const float hi = p.rna ? tf32_rna(x) : __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        const uint32_t o = p.a_mn ? off_mnmajor(M, r, k) : off_kmajor(M, r, k, p.swap);
+        const uint32_t o = p.a_mn ? off_mnmajor(M, r, k) : off_kmajor(M, r, k, p.swap, p.pad);
         Ahi[o / 4] = hi;
         Alo[o / 4] = p.rna ? tf32_rna(x - hi) : x - hi;
     }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
         const int r = idx / K, k = idx % K;
         const float x = p.B[idx];
         const float hi = p.rna ? tf32_rna(x) : __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        const uint32_t o = p.b_mn ? off_mnmajor(N, r, k) : off_kmajor(N, r, k, p.swap);
+        const uint32_t o = p.b_mn ? off_mnmajor(N, r, k) : off_kmajor(N, r, k, p.swap, p.pad);
         Bhi[o / 4] = hi;
         Blo[o / 4] = p.rna ? tf32_rna(x - hi) : x - hi;
     }
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     // MN-major: SBO = stride between 4-row groups, LBO = stride between 8-k groups
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_step, b_step;
     if (p.a_mn) { a_sbo = 128; a_lbo = (M / 4) * 128; a_step = a_lbo; }
-    else { a_sbo = p.swap ? (K / 4) * 128 : 128; a_lbo = p.swap ? 128 : (M / 8) * 128; a_step = 2 * a_lbo; }
+    else { a_sbo = p.swap ? (K / 4) * 128 : 128; a_lbo = p.swap ? 128 : (M / 8) * 128 + p.pad; a_step = 2 * a_lbo; }
     if (p.b_mn) { b_sbo = 128; b_lbo = (uint32_t)(N / 4) * 128; b_step = b_lbo; }
-    else { b_sbo = p.swap ? (K / 4) * 128 : 128; b_lbo = p.swap ? 128 : (uint32_t)(N / 8) * 128; b_step = 2 * b_lbo; }
+    else { b_sbo = p.swap ? (K / 4) * 128 : 128; b_lbo = p.swap ? 128 : (uint32_t)(N / 8) * 128 + p.pad; b_step = 2 * b_lbo; }
     if (p.swap_desc) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
 
     long long t0 = 0, t1 = 0;
@@ -178,36 +178,36 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
 
 int main() {
     const int M = 128, K = 64;
-    std::vector<float> hA(M * K), hBfull(192 * K);
+    std::vector<float> hA(M * K), hBfull(256 * K);
     srand(1);
     for (auto& x : hA) x = (float)rand() / RAND_MAX * 2.f - 1.f;
     for (auto& x : hBfull) x = (float)rand() / RAND_MAX * 2.f - 1.f;
     float *dA, *dB, *dD;
     long long* dC;
     int* dF;
-    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dB, hBfull.size() * 4); cudaMalloc(&dD, M * 192 * 4);
+    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dB, hBfull.size() * 4); cudaMalloc(&dD, M * 256 * 4);
     cudaMalloc(&dC, 8); cudaMalloc(&dF, 4);
     cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hBfull.data(), hBfull.size() * 4, cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 
-    struct Case { const char* name; int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna; };
+    struct Case { const char* name; int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad; };
     const Case cases[] = {
-        {"K-major A,B  N=192 1xTF32", 192, 1, 0, 0, 0, 0, 1},
-        {"K-major A,B  N=192 3xTF32", 192, 3, 0, 0, 0, 0, 1},
-        {"K-major A,B  N=192 3xTF32 rna split", 192, 3, 0, 0, 0, 0, 1, 1},
-        {"MN-major A,B N=96  3xTF32 rna split", 96, 3, 1, 1, 0, 0, 1, 1},
-        {"K-major (layout swapped: K chunks adjacent) 3x", 192, 3, 0, 0, 1, 0, 1},
-        {"MN-major A,B N=96  3xTF32", 96, 3, 1, 1, 0, 0, 1},
-        {"MN-major A, K-major B N=192 3x", 192, 3, 1, 0, 0, 0, 1},
-        {"K-major N=192 3x timing reps=64", 192, 3, 0, 0, 0, 0, 64},
-        {"MN-major N=96 3x timing reps=64", 96, 3, 1, 1, 0, 0, 64},
+        {"K-major N=192 3xTF32 (correctness)", 192, 3, 0, 0, 0, 0, 1, 1, 0},
+        {"K-major N=96 3xTF32 padded LBO+16 (correctness)", 96, 3, 0, 0, 0, 0, 1, 1, 16},
+        {"K-major N=192 timing reps=64", 192, 3, 0, 0, 0, 0, 64, 1, 0},
+        {"K-major N=192 timing reps=64 padded", 192, 3, 0, 0, 0, 0, 64, 1, 16},
+        {"K-major N=96 timing reps=64", 96, 3, 0, 0, 0, 0, 64, 1, 0},
+        {"K-major N=96 timing reps=64 padded LBO+16", 96, 3, 0, 0, 0, 0, 64, 1, 16},
+        {"K-major N=96 timing reps=64 swapped layout (K chunks adjacent)", 96, 3, 0, 0, 1, 0, 64, 1, 0},
+        {"K-major N=64 timing reps=64", 64, 3, 0, 0, 0, 0, 64, 1, 0},
+        {"K-major N=256 timing reps=64", 256, 3, 0, 0, 0, 0, 64, 1, 0},
     };
     for (const Case& c : cases) {
-        Params p{dA, dB, dD, c.N, c.passes, c.a_mn, c.b_mn, c.swap, c.swap_desc, c.reps, c.rna, dC, dF};
+        Params p{dA, dB, dD, c.N, c.passes, c.a_mn, c.b_mn, c.swap, c.swap_desc, c.reps, c.rna, c.pad, dC, dF};
         cudaMemset(dF, 0, 4);
-        cudaMemset(dD, 0, M * 192 * 4);
-        const size_t smem = (size_t)(2 * M * K + 2 * c.N * K) * 4 + 1024;
+        cudaMemset(dD, 0, M * 256 * 4);
+        const size_t smem = (size_t)(2 * M * K + 2 * c.N * K) * 4 + 1024 + 4 * 16 * 64;
         umma_test_kernel<<<1, 128, smem>>>(p);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%-52s CUDA error: %s\n", c.name, cudaGetErrorString(e)); return 1; }
