@@ -523,24 +523,28 @@ __global__ void __launch_bounds__(128) f4tc_phys_kernel(const StepArgs a, const 
 
 // ---------------------------------------------------------------------------------------------------------------
 // dW kernel: partials[cta][k*AW + a] = sum over the CTA's envs of phi_k(s_env) * d_a(env), d_a = coef if a == action.
-// CTA = 512 threads; sub-tile = 32 envs; thread = (env lane, q = warp 0..15): A rows m = i0*16 + i1*2 + b with
-// i0 = q/2, i1 in 4(q%2)..+3; B rows n = a*32 + i2'*8 + i3 with i3 = q/2, i2' in 2(q%2)..+1.  K index = (part, env):
-// two units per sub-tile (real, imaginary), double-buffered so that generating one unit overlaps the MMAs of the other.
-// The accumulator stays in TMEM for the whole kernel.
+// CTA = 16 generator warps + 1 MMA-issuer warp; sub-tile = 32 envs; generator thread = (env lane, q = warp 0..15):
+// A rows m = i0*16 + i1*2 + b with i0 = q/2, i1 in 4(q%2)..+3; B rows n = a*32 + i2'*8 + i3 with i3 = q/2, i2' in
+// 2(q%2)..+1.  K index = (part, env): two units per sub-tile (real, imaginary), double-buffered: the generators publish
+// a unit (full barrier), the issuer queues its MMAs and commits them (done barrier) while the next unit is generated.
+// 3xTF32 in two MMAs per K step: A_hi x [B_hi; B_lo] (N = 2 NB: hi*hi and hi*lo land in separate column ranges) and
+// A_lo x B_hi (N = NB) — an SS-mode MMA costs >= 70 cycles for its A fetch whatever N is (tools/microbench), so
+// folding the third pass into a wider second operand saves a third of the tensor time.  The accumulator stays in TMEM
+// for the whole kernel; the two column ranges are added in the epilogue.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW>
 struct F4tcDwSmem {
     static constexpr int NB = AW * 32;
     static constexpr uint32_t A_LBO = 16 * 128 + 16;        // +16 B: the 8 K chunks of a warp's scalar stores hit 8 distinct bank groups
-    static constexpr uint32_t B_LBO = (NB / 8) * 128 + 16;
+    static constexpr uint32_t B_LBO = (2 * NB / 8) * 128 + 16;  // B tile rows: [0, NB) = hi part, [NB, 2 NB) = lo part
     static constexpr int A_FLOATS = 8 * A_LBO / 4;          // one of {hi, lo}: 8 K chunks (32 envs)
-    static constexpr int B_FLOATS = 8 * B_LBO / 4;
-    static constexpr int UNIT_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
+    static constexpr int B_FLOATS = 8 * B_LBO / 4;          // hi and lo rows together
+    static constexpr int UNIT_FLOATS = 2 * A_FLOATS + B_FLOATS;
     static constexpr size_t bytes = (size_t)(2 * UNIT_FLOATS) * sizeof(float);
 };
 
 template <int DOM>
-__global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float* __restrict__ tabs_g, const float* __restrict__ coef,
+__global__ void __launch_bounds__(544, 1) f4tc_dw_kernel(int64_t n, const float* __restrict__ tabs_g, const float* __restrict__ coef,
                                                          const int32_t* __restrict__ actions, float* __restrict__ partials, Counters* counters,
                                                          long long* phase_prof) {
     using Dom = Domain<DOM>;
@@ -548,12 +552,13 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
     using SM = F4tcDwSmem<AW>;
     constexpr int NB = SM::NB;
     constexpr uint32_t SBO = 128;
-    constexpr uint32_t IDESC = tc::make_idesc(128, NB);
-    constexpr int TMEM_COLS = 128;
+    constexpr uint32_t IDESC_WIDE = tc::make_idesc(128, 2 * NB), IDESC_HALF = tc::make_idesc(128, NB);
+    constexpr int TMEM_COLS = 256;  // 2 NB <= 192 accumulator columns
 
     extern __shared__ __align__(128) unsigned char f4tc_smem[];
     float* units = reinterpret_cast<float*>(f4tc_smem);
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[2];   // done[part]: the MMAs of the unit in buffer `part` completed
+    __shared__ __align__(8) unsigned long long fulls[2];  // full[part]: all 512 generator threads stored their elements
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5, qi = q >> 1, hq = q & 1;
@@ -563,6 +568,8 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
     if (tid == 0) {
         tc::mbar_init(tc::smem_u32(&bars[0]), 1);
         tc::mbar_init(tc::smem_u32(&bars[1]), 1);
+        tc::mbar_init(tc::smem_u32(&fulls[0]), 512);
+        tc::mbar_init(tc::smem_u32(&fulls[1]), 512);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::fence_before_sync();
@@ -574,7 +581,34 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
     const int64_t s_begin = n_sub * blockIdx.x / gridDim.x, s_end = n_sub * (blockIdx.x + 1) / gridDim.x;
     uint32_t ph[2] = {0, 0};
     bool used[2] = {false, false};
-    bool first_mma = true;
+
+    if (q == 16) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            uint32_t phf[2] = {0, 0};
+            bool first_mma = true;
+            for (int64_t st = s_begin; st < s_end; ++st) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const float* Ahi = units + part * SM::UNIT_FLOATS;
+                    const float* Alo = Ahi + SM::A_FLOATS;
+                    const float* Bt = Alo + SM::A_FLOATS;
+                    tc::mbar_wait(tc::smem_u32(&fulls[part]), phf[part], fault);
+                    phf[part] ^= 1;
+                    tc::fence_after_sync();
+                    const uint32_t bbase = tc::smem_u32(Bt);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bd = tc::make_desc(bbase + ks * 2 * SM::B_LBO, SM::B_LBO, SBO);
+                        tc::umma_tf32(tmem, tc::make_desc(tc::smem_u32(Ahi) + ks * 2 * SM::A_LBO, SM::A_LBO, SBO), bd, IDESC_WIDE, first_mma ? 0u : 1u);
+                        tc::umma_tf32(tmem, tc::make_desc(tc::smem_u32(Alo) + ks * 2 * SM::A_LBO, SM::A_LBO, SBO), bd, IDESC_HALF, 1u);
+                        first_mma = false;
+                    }
+                    tc::umma_commit(tc::smem_u32(&bars[part]));
+                }
+            }
+        }
+    } else {
     // float offsets of this thread's element (k = lane) in its rows
     const int ka = (lane >> 2) * (int)(SM::A_LBO / 4) + (lane & 3);
     const int kb = (lane >> 2) * (int)(SM::B_LBO / 4) + (lane & 3);
@@ -635,8 +669,8 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
         for (int part = 0; part < 2; ++part) {
             float* Ahi = units + part * SM::UNIT_FLOATS;
             float* Alo = Ahi + SM::A_FLOATS;
-            float* Bhi = Alo + SM::A_FLOATS;
-            float* Blo = Bhi + SM::B_FLOATS;
+            float* Bhi = Alo + SM::A_FLOATS;   // rows [0, NB)
+            float* Blo = Bhi + (NB / 8) * 32;  // rows [NB, 2 NB) of the same tile
             if (used[part]) { tc::mbar_wait(tc::smem_u32(&bars[part]), ph[part], fault); ph[part] ^= 1; }
             used[part] = true;
             mark(1);
@@ -661,22 +695,7 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
             mark(2);
             tc::fence_async_smem();
             tc::fence_before_sync();
-            __syncthreads();
-            mark(3);
-            if (tid == 0) {
-                tc::fence_after_sync();
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t abase = tc::smem_u32(pass == 1 ? Alo : Ahi), bbase = tc::smem_u32(pass == 2 ? Blo : Bhi);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        tc::umma_tf32(tmem, tc::make_desc(abase + ks * 2 * SM::A_LBO, SM::A_LBO, SBO),
-                                      tc::make_desc(bbase + ks * 2 * SM::B_LBO, SM::B_LBO, SBO), IDESC, first_mma ? 0u : 1u);
-                        first_mma = false;
-                    }
-                }
-                tc::umma_commit(tc::smem_u32(&bars[part]));
-            }
+            tc::mbar_arrive(tc::smem_u32(&fulls[part]));  // publish: the issuer warp queues this unit's MMAs
             mark(4);
         }
         cur = nxt;
@@ -685,12 +704,13 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
 #pragma unroll
         for (int x = 0; x < 8; ++x) phase_prof[(size_t)blockIdx.x * 8 + x] += prof[x];
     }
+    }  // generator warps
 
     // ---- drain + epilogue: TMEM [m = i0*16 + i1*2 + b][n = a*32 + i2'*8 + i3] -> partials[cta][k*AW + a] ----
     float* out = partials + (size_t)blockIdx.x * 4096 * AW;
     if (s_begin >= s_end) {
-        for (int j = tid; j < 4096 * AW; j += 512) out[j] = 0.0f;
-    } else {
+        for (int j = tid; j < 4096 * AW; j += 544) out[j] = 0.0f;
+    } else if (q < 16) {
 #pragma unroll
         for (int part = 0; part < 2; ++part)
             if (used[part]) { tc::mbar_wait(tc::smem_u32(&bars[part]), ph[part], fault); ph[part] ^= 1; }
@@ -700,13 +720,14 @@ __global__ void __launch_bounds__(512, 1) f4tc_dw_kernel(int64_t n, const float*
             const int m = q * 32 + lane, i0 = m >> 4, i1 = (m >> 1) & 7, b = m & 1;
 #pragma unroll
             for (int c = 0; c < AW; ++c) {
-                float v[32];
+                float v[32], w[32];  // hi*hi + lo*hi columns, hi*lo columns
                 tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(NB + c * 32), w);
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
                     const int i2 = 4 * b + (x >> 3), i3 = x & 7;
                     const int k = ((i0 * 8 + i1) * 8 + i2) * 8 + i3;
-                    out[(size_t)k * AW + c] = v[x];
+                    out[(size_t)k * AW + c] = v[x] + w[x];
                 }
             }
         }

@@ -48,7 +48,7 @@ static cudaError_t dw_one(int64_t n, const float* tabs, const void* coef, const 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, 512, smem, st>>>(n, tabs, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters, prof);
+    kern<<<grid, 544, smem, st>>>(n, tabs, static_cast<const float*>(coef), actions, static_cast<float*>(partials), counters, prof);
     return cudaGetLastError();
 }
 
