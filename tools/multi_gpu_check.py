@@ -47,6 +47,42 @@ for dtype, tol, horizon in ((abi.F64, 1e-11, None), (abi.F32, 1e-4, 12)):
             single.close()
         eng.close()
         dist.barrier()
+# BASELINE config 4: Acrobot / ExpectedSARSA / Fourier(7) on the tensor-core path, envs sharded over the ranks, dW (4096 x 3)
+# summed with ncclAllReduce between the dW pass and the weight update
+from rsrl_b200.engine import comm_unique_id
+import time
+for n_global, steps in ((3001, 6), (131072 * world, 10)):
+    kw = dict(domain=abi.ACROBOT, basis_order=7, algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, dtype=abi.F32,
+              init_mode=abi.INIT_UNIFORM, init_lo=[-0.1] * 4, init_hi=[0.1] * 4, max_episode_steps=500, seed=3, gamma=0.99, lr=1e-3,
+              alpha=1.0, update_scale=abi.SCALE_MEAN)
+    lo, hi = shard_range(n_global, rank, world)
+    eng = Engine(abi.default_config(n_envs=hi - lo, env_offset=lo, n_envs_global=n_global, device=local, **kw))
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)
+    dist.barrier()
+    eng.step(2); eng.sync(); dist.barrier()
+    t0 = time.perf_counter(); eng.step(steps - 2); eng.sync(); dist.barrier(); dt = time.perf_counter() - t0
+    W = torch.from_numpy(eng.weights()).cuda()
+    allW = [torch.empty_like(W) for _ in range(world)]
+    dist.all_gather(allW, W)
+    replicas_identical = all(bool((w == allW[0]).all()) for w in allW)
+    if rank == 0:
+        good = replicas_identical
+        msg = ""
+        if n_global <= 4096:
+            single = Engine(abi.default_config(n_envs=n_global, device=local, **kw))
+            single.step(steps); single.sync()
+            werr = np.abs(eng.weights() - single.weights()).max() / max(np.abs(single.weights()).max(), 1e-30)
+            good &= werr < 1e-4
+            msg = f" |W - W_single|/|W|max={werr:.3e}"
+            single.close()
+        else:
+            msg = f" {1e6 * dt / (steps - 2):.1f} us/step  {n_global * (steps - 2) / dt / 1e9:.3f} G env-steps/s"
+        ok &= good
+        print(f"cfg4 f32 N={n_global} world={world}: replicas_identical={replicas_identical}{msg} -> {'OK' if good else 'FAIL'}", flush=True)
+    eng.close()
+    dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
