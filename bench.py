@@ -281,6 +281,46 @@ def main():
         out["also"] = {"per_env_weights": pe,
                        "f64": side_run("SHARED weights, all arithmetic f64 (parity anchor dtype)", dtype=abi.F64)}
 
+        # ---- the other BASELINE configs at their per-GPU shard size (parity-test cases; reported for context) ----
+        def cfg_run(label, k, n_envs, **kw):
+            base = dict(n_envs=n_envs, dtype=dtype, init_mode=abi.INIT_UNIFORM, seed=0, update_scale=abi.SCALE_MEAN)
+            base.update(kw)
+            with Engine(abi.default_config(**base)) as e3:
+                st3 = torch.cuda.ExternalStream(e3.stream(), device=torch.device("cuda", local_rank))
+                e3.step(max(3, k // 10))
+                e3.sync()
+                flush.zero_()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(st3)
+                e3.step(k)
+                a1.record(st3)
+                a1.synchronize()
+                ms3 = a0.elapsed_time(a1)
+                return {"value": n_envs * k / (ms3 * 1e-3), "unit": "env-steps/s", "us_per_batched_step": 1e3 * ms3 / k, "what": label}
+        c3 = cfg_run("cfg3: CartPole SARSA TileCoding(8 tilings, 8 tiles/dim, 4096 rows) eps-greedy, 262144 envs, SHARED", 300, 262144,
+                     domain=abi.CART_POLE, basis=abi.TILE_CODING, algo=abi.SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99,
+                     lr=0.1 / 8, init_lo=[-0.05] * 4, init_hi=[0.05] * 4, max_episode_steps=500)
+        c3["roofline"] = {"bound": "hbm", "achieved": 80 * c3["value"] / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 80 * c3["value"] / 1e9 / peak_gbs,
+                          "note": "algorithmic 80 B/env-step (SURVEY 8d); binding roof: f64 RK4 latency at 16 warps/SM (profiles/r01_final.md)"}
+        c4 = cfg_run("cfg4 shard: Acrobot ExpectedSARSA Fourier(7)+bias (F=4096) eps-greedy, 131072 envs, SHARED, tcgen05 3xTF32 path", 40, 131072,
+                     domain=abi.ACROBOT, basis_order=7, algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=1e-4,
+                     alpha=1.0, init_lo=[-0.1] * 4, init_hi=[0.1] * 4, max_episode_steps=500)
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        # per env-step: algorithmic 3 contractions x 2*4096*3; executed 3 TF32 passes x (2 evaluations x {re,im} x 192x64 MACs + {re,im} x 128x96 MACs) x 2
+        alg_flop, exe_flop = 3 * 2 * 4096 * 3, 3 * (2 * 2 * 192 * 64 * 2 + 2 * 128 * 96 * 2)
+        c4["roofline"] = {"bound": "tensor", "achieved": alg_flop * c4["value"] / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                          "frac": alg_flop * c4["value"] / 1e12 / tf32_peak, "executed_tflops": exe_flop * c4["value"] / 1e12,
+                          "note": "algorithmic 73.7 kFLOP/env-step (two Q = Phi W evaluations + dW = Phi^T D, SURVEY 8d); peak = measured bf16 "
+                                  "cuBLAS TFLOP/s / 2 (kind::tf32 runs at half the bf16 rate); executed = 3xTF32 passes over the complex "
+                                  "(real, imaginary) split, 6x the algorithmic count; see profiles/r01_f4tc.md"}
+        c5 = cfg_run("cfg5 shard: MountainCar SARSA(lambda) replacing traces Fourier(5) eps-greedy, 32768 envs, per-env traces in shared memory", 1000, 32768,
+                     algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99, init_lo=[-0.6, 0.0],
+                     init_hi=[-0.4, 0.0], max_episode_steps=1000)
+        c5["roofline"] = {"bound": "hbm", "achieved": 912 * c5["value"] / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 912 * c5["value"] / 1e9 / peak_gbs,
+                          "note": "algorithmic 912 B/env-step (state + read/write 108 trace values); traces never leave shared memory"}
+        out["also"].update({"cfg3_tile_coding": c3, "cfg4_fourier7_tensor_core": c4, "cfg5_sarsa_lambda": c5})
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as O
         O.build()

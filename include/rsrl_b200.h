@@ -60,10 +60,11 @@ typedef enum rsrl_status {
 typedef enum rsrl_domain { RSRL_MOUNTAIN_CAR = 0, RSRL_CART_POLE = 1, RSRL_ACROBOT = 2 } rsrl_domain_t;
 /* lfa::basis::{Fourier, Polynomial, TileCoding} (+ .with_bias()) */
 typedef enum rsrl_basis { RSRL_FOURIER = 0, RSRL_POLYNOMIAL = 1, RSRL_TILE_CODING = 2 } rsrl_basis_t;
-/* rsrl/src/control/td/{q_learning,sarsa,expected_sarsa,sarsa_lambda,q_lambda}.rs, rsrl/src/prediction/td/{td,td_lambda}.rs */
+/* rsrl/src/control/td/{q_learning,sarsa,expected_sarsa,sarsa_lambda,q_lambda,pal}.rs, rsrl/src/prediction/td/{td,td_lambda}.rs */
 typedef enum rsrl_algo {
     RSRL_QLEARNING = 0, RSRL_SARSA = 1, RSRL_EXPECTED_SARSA = 2,
-    RSRL_SARSA_LAMBDA = 3, RSRL_Q_LAMBDA = 4, RSRL_TD_LAMBDA = 5, RSRL_TD0 = 6
+    RSRL_SARSA_LAMBDA = 3, RSRL_Q_LAMBDA = 4, RSRL_TD_LAMBDA = 5, RSRL_TD0 = 6,
+    RSRL_PAL = 7 /* persistent advantage learning, control/td/pal.rs:35-59 (update error = alpha * residual) */
 } rsrl_algo_t;
 /* rsrl/src/policies/{greedy,epsilon_greedy,random}.rs */
 typedef enum rsrl_policy { RSRL_GREEDY = 0, RSRL_EPSILON_GREEDY = 1, RSRL_RANDOM = 2 } rsrl_policy_t;
@@ -103,7 +104,7 @@ typedef struct rsrl_config {
     int64_t  max_episode_steps; /* 0 = uncapped like examples/q_learning.rs:40 */
     uint64_t seed;
     double   lr;                /* SGD(lr) of the LFA (examples/q_learning.rs:25) */
-    double   alpha;             /* agent step size: ExpectedSARSA (expected_sarsa.rs:64), lambda agents */
+    double   alpha;             /* agent step size: ExpectedSARSA (expected_sarsa.rs:64), PAL (pal.rs:49-57), lambda agents */
     double   gamma;
     double   lambda;
     double   epsilon;

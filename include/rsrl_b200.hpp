@@ -210,5 +210,9 @@ struct SARSA : TDAgent { SARSA(std::shared_ptr<LFA> q, double gamma) : TDAgent(s
 struct ExpectedSARSA : TDAgent {
     ExpectedSARSA(std::shared_ptr<LFA> q, double alpha, double gamma) : TDAgent(std::move(q), gamma, RSRL_EXPECTED_SARSA, alpha) {}
 };
+// rsrl/src/control/td/pal.rs:18-24
+struct PAL : TDAgent {
+    PAL(std::shared_ptr<LFA> q, double alpha, double gamma) : TDAgent(std::move(q), gamma, RSRL_PAL, alpha) {}
+};
 
 }  // namespace rsrl

@@ -551,6 +551,8 @@ static double agent_handle(orc_engine_t* e, int64_t i, int64_t g, uint64_t draw,
 
     double* qs = evaluate_alloc(c, W, A, from); /* Shared<LFA>::evaluate_index = evaluate(args)[index] (core.rs:79-83) */
     double qsa = qs[a];
+    int a_star = orc_argmax_first(qs, A, NULL); /* pal.rs:47 */
+    double q_astar = qs[a_star];
 
     if (c->algo == RSRL_Q_LAMBDA && z) { /* q_lambda.rs:68 */
         if (a != orc_argmax_first(qs, A, NULL)) memset(z, 0, (size_t)(e->F * A) * sizeof(double));
@@ -581,6 +583,12 @@ static double agent_handle(orc_engine_t* e, int64_t i, int64_t g, uint64_t draw,
             if (nf) e->st.nonfinite = 1;
             free(nq2);
             residual = r + c->gamma * nq[na] - qsa;
+        } else if (c->algo == RSRL_PAL) { /* pal.rs:44-52: td_error bootstraps from nqs[a_star] (a_star = argmax_first Q(s)) */
+            int na_star = orc_argmax_first(nq, A, NULL);
+            double td_error = r + c->gamma * nq[a_star] - qsa;
+            double al_error = td_error - c->alpha * (q_astar - qsa);
+            double alt = td_error - c->alpha * (nq[na_star] - nq[a]);
+            residual = fmax(al_error, alt);
         } else { /* expected_sarsa.rs:52-58 */
             double p[16], exp_nv = 0.0;
             double* nq2 = evaluate_alloc(c, W, A, to);
@@ -602,7 +610,7 @@ static double agent_handle(orc_engine_t* e, int64_t i, int64_t g, uint64_t draw,
         }
         return residual;
     }
-    err = c->algo == RSRL_EXPECTED_SARSA ? c->alpha * residual : residual; /* expected_sarsa.rs:64 */
+    err = (c->algo == RSRL_EXPECTED_SARSA || c->algo == RSRL_PAL) ? c->alpha * residual : residual; /* expected_sarsa.rs:64, pal.rs:57 */
     {
         double* phi = project_alloc(c, from); /* update_index re-projects (fa/linear.rs:389) */
         accumulate_col(e, dst, a, (c->lr * err) / e->step_scale, phi);

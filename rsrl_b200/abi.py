@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "librsrl_b200.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ENONFINITE, ECOMM, ENODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
 MOUNTAIN_CAR, CART_POLE, ACROBOT = 0, 1, 2
 FOURIER, POLYNOMIAL, TILE_CODING = 0, 1, 2
-QLEARNING, SARSA, EXPECTED_SARSA, SARSA_LAMBDA, Q_LAMBDA, TD_LAMBDA, TD0 = range(7)
+QLEARNING, SARSA, EXPECTED_SARSA, SARSA_LAMBDA, Q_LAMBDA, TD_LAMBDA, TD0, PAL = range(8)
 GREEDY, EPSILON_GREEDY, RANDOM = 0, 1, 2
 TRACE_ACCUMULATE, TRACE_REPLACE, TRACE_DUTCH = 0, 1, 2
 SHARED, PER_ENV = 0, 1

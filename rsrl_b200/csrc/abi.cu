@@ -64,7 +64,7 @@ static int validate(const rsrl_config_t* c) {
     if (c->struct_size != sizeof(rsrl_config_t)) return fail(RSRL_EINVAL, "rsrl_config_t.struct_size mismatch (ABI)");
     if (c->domain < 0 || c->domain > 2) return fail(RSRL_EINVAL, "unknown domain");
     if (c->basis < 0 || c->basis > 2) return fail(RSRL_EINVAL, "unknown basis");
-    if (c->algo < 0 || c->algo > RSRL_TD0) return fail(RSRL_EINVAL, "unknown algo");
+    if (c->algo < 0 || c->algo > RSRL_PAL) return fail(RSRL_EINVAL, "unknown algo");
     if (c->policy < 0 || c->policy > 2) return fail(RSRL_EINVAL, "unknown policy");
     if (c->dtype != RSRL_F32 && c->dtype != RSRL_F64) return fail(RSRL_EINVAL, "unknown dtype");
     if (c->weight_mode != RSRL_SHARED && c->weight_mode != RSRL_PER_ENV) return fail(RSRL_EINVAL, "unknown weight_mode");
@@ -497,6 +497,10 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         if (e->pblock > 512) e->pblock = 512;
         if (e->pblock < 64) e->pblock = 64;
         e->psmem = (size_t)e->FA * e->rsz;
+        // dense variant: W + a 64-bit accumulator table per CTA in shared memory (RSRL_B200_TILE_DENSE=0 keeps the RED-atomics kernel)
+        const size_t dense_smem = (size_t)e->FA * (e->rsz + sizeof(unsigned long long));
+        e->targs.dense = dense_smem <= 200 * 1024 && !(getenv("RSRL_B200_TILE_DENSE") && atoi(getenv("RSRL_B200_TILE_DENSE")) == 0);
+        if (e->targs.dense) e->psmem = dense_smem;
         e->grid = 1; e->block = 64; e->smem = 0;
     } else {
         choose_launch(e);
@@ -525,7 +529,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     if (e->tile) {
         e->targs.tp = tile_params(cfg);
         e->targs.fx_scale = cfg->dtype == RSRL_F32 ? 1099511627776.0 : 17592186044416.0;  // 2^40 / 2^44
-        e->tileG_bytes = (size_t)4 * e->FA * sizeof(unsigned long long);
+        e->tileG_bytes = (size_t)(e->targs.dense ? e->pgrid + 1 : 4) * e->FA * sizeof(unsigned long long);
         E_TRY(cudaMalloc(&e->targs.G, e->tileG_bytes));
         E_TRY(cudaMalloc(&e->targs.barrier, sizeof(unsigned long long)));
     } else if (e->f4) {
@@ -642,6 +646,7 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
             e->targs.barrier_base = e->tile_steps;
+            if (e->targs.dense) CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), e->stream));  // launch-local targets
             auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;
             CU_TRY(fn(e->cfg.domain, e->AW, false, a, k, e->targs, e->pgrid, e->pblock, e->psmem, e->stream));
             e->launches += 1;
@@ -884,6 +889,7 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
         if (rc) return rc;
     } else if (e->tile) {
         e->targs.barrier_base = e->tile_steps;
+        if (e->targs.dense) CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
         int g2 = (int)((n + 127) / 128);
         if (g2 > e->pgrid) g2 = e->pgrid;
         auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;

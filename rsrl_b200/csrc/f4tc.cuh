@@ -438,8 +438,9 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
         if (active) {
             // ---- D: TD error with W_t (kernels.cuh:env_core); Q(s') was evaluated for every row, terminal rows ignore it ----
             const float4 aux = reinterpret_cast<const float4*>(fa.aux)[i];   // {Q(s_t)[a_t], reward, terminal, -} from the physics kernel
-            const float qsa = aux.x, reward = aux.y;
-            const bool terminated = aux.z != 0.0f;
+            const float qsa = aux.x, reward = aux.y, q_astar = aux.w;
+            const int tz = (int)aux.z, a_star = tz >> 1;
+            const bool terminated = (tz & 1) != 0;
             bool nonfinite = false;
             float residual;
             if (terminated) {
@@ -453,6 +454,17 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
                     target = q[0];
 #pragma unroll
                     for (int c = 0; c < AW; ++c) if (c == na) target = q[c];
+                } else if (a.algo == RSRL_PAL) {  // pal.rs:44-52 (q = Q(s'))
+                    const int na_star = argmax_first<float, AW>(q), act = a.actions[i];
+                    float nq_astar = q[0], nq_nastar = q[0], nq_act = q[0];
+#pragma unroll
+                    for (int c = 0; c < AW; ++c) {
+                        if (c == a_star) nq_astar = q[c];
+                        if (c == na_star) nq_nastar = q[c];
+                        if (c == act) nq_act = q[c];
+                    }
+                    const float td_error = reward + (float)a.gamma * nq_astar - qsa;
+                    target = fmaxf(td_error - (float)a.alpha * (q_astar - qsa), td_error - (float)a.alpha * (nq_nastar - nq_act));
                 } else {
                     float p[AW];
                     policy_probs<float, AW>(a.pol.policy, (float)a.epsilon, q, p);
@@ -460,9 +472,9 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
 #pragma unroll
                     for (int c = 0; c < AW; ++c) target = target + q[c] * p[c];
                 }
-                residual = reward + (float)a.gamma * target - qsa;
+                residual = a.algo == RSRL_PAL ? target : reward + (float)a.gamma * target - qsa;
             }
-            const float coef = a.algo == RSRL_EXPECTED_SARSA ? (float)a.lr_scaled * ((float)a.alpha * residual) : (float)a.lr_scaled * residual;
+            const float coef = (a.algo == RSRL_EXPECTED_SARSA || a.algo == RSRL_PAL) ? (float)a.lr_scaled * ((float)a.alpha * residual) : (float)a.lr_scaled * residual;
             if (a.td) static_cast<float*>(a.td)[i] = residual;
             if (nonfinite) atomicExch(&a.counters->nonfinite, 1);
             static_cast<float*>(fa.coef)[i] = coef;
@@ -516,7 +528,12 @@ __global__ void __launch_bounds__(128) f4tc_phys_kernel(const StepArgs a, const 
     for (int c = 0; c < AW; ++c) if (c == act) qsa = q[c];
 #pragma unroll
     for (int d = 0; d < D; ++d) fa.next_states[i * D + d] = s[d];
-    reinterpret_cast<float4*>(fa.aux)[i] = make_float4(qsa, (float)reward, terminated ? 1.0f : 0.0f, 0.0f);
+    // PAL (pal.rs:44-50) also needs a* = argmax_first Q(s_t) and Q(s_t)[a*]: packed as terminal + 2 a*, Q(s_t)[a*]
+    const int a_star = argmax_first<float, AW>(q);
+    float q_astar = q[0];
+#pragma unroll
+    for (int c = 0; c < AW; ++c) if (c == a_star) q_astar = q[c];
+    reinterpret_cast<float4*>(fa.aux)[i] = make_float4(qsa, (float)reward, (terminated ? 1.0f : 0.0f) + 2.0f * (float)a_star, q_astar);
     a.actions[i] = act;  // (EXT: the caller's action, consumed by the dW pass)
     if (nonfinite) atomicExch(&a.counters->nonfinite, 1);
 }

@@ -131,6 +131,20 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
             target = nq[0];
 #pragma unroll
             for (int c = 0; c < AW; ++c) if (c == na) target = nq[c];
+        } else if (a.algo == RSRL_PAL) {                                                          // pal.rs:44-52 (literal: nqs[a_star])
+            const int a_star = argmax_first<R, AW>(q), na_star = argmax_first<R, AW>(nq);
+            R nq_astar = nq[0], q_astar = q[0], nq_nastar = nq[0], nq_act = nq[0];
+#pragma unroll
+            for (int c = 0; c < AW; ++c) {
+                if (c == a_star) { nq_astar = nq[c]; q_astar = q[c]; }
+                if (c == na_star) nq_nastar = nq[c];
+                if (c == o.act) nq_act = nq[c];
+            }
+            const R td_error = (R)reward + (R)a.gamma * nq_astar - qsa;
+            const R al_error = td_error - (R)a.alpha * (q_astar - qsa);
+            const R alt = td_error - (R)a.alpha * (nq_nastar - nq_act);
+            o.residual = (al_error > alt || alt != alt) ? al_error : alt;                                // f64::max (pal.rs:52)
+            target = (R)0;
         } else {                                                                                  // expected_sarsa.rs:52-56
             R p[AW];
             policy_probs<R, AW>(a.pol.policy, (R)a.epsilon, nq, p);
@@ -138,11 +152,11 @@ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t
 #pragma unroll
             for (int c = 0; c < AW; ++c) target = target + nq[c] * p[c];
         }
-        o.residual = (R)reward + (R)a.gamma * target - qsa;
+        if (a.algo != RSRL_PAL) o.residual = (R)reward + (R)a.gamma * target - qsa;
     }
     if (a.algo == RSRL_SARSA_LAMBDA || a.algo == RSRL_Q_LAMBDA) o.coef = (R)(a.alpha * a.inv_scale) * o.residual;  // bypasses SGD lr
     else if (a.algo == RSRL_TD_LAMBDA) o.coef = (R)a.inv_scale * o.residual;                                       // td_lambda.rs:56-59
-    else if (a.algo == RSRL_EXPECTED_SARSA) o.coef = (R)a.lr_scaled * ((R)a.alpha * o.residual);                   // expected_sarsa.rs:64
+    else if (a.algo == RSRL_EXPECTED_SARSA || a.algo == RSRL_PAL) o.coef = (R)a.lr_scaled * ((R)a.alpha * o.residual);  // expected_sarsa.rs:64, pal.rs:57
     else o.coef = (R)a.lr_scaled * o.residual;
 }
 

@@ -15,8 +15,8 @@ namespace rsrl {
 
 struct TileArgs {
     TileParams tp;
-    int pad;
-    unsigned long long* G;        // [4][M * AW] fixed-point dW accumulators
+    int dense;                    // 1: tile_dense_kernel (per-CTA shared-memory accumulation + dense reduce-scatter), 0: RED atomics
+    unsigned long long* G;        // RED path: [4][M * AW] fixed-point dW accumulators; dense path: [grid + 1][M * AW] partials + totals
     unsigned long long* barrier;  // monotonically increasing arrival counter
     unsigned long long barrier_base;  // batched steps (fused or handle) completed before this launch: barrier target
                                       // and rotation index of the dW tables
@@ -114,6 +114,137 @@ __global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs 
             Wsm[j] += (R)((double)v * inv_fx);
         }
         for (int j = b * BLOCK + tid; j < MA; j += G * BLOCK) Gz[j] = 0ull;
+        __syncthreads();
+    }
+    if (b == 0)
+        for (int j = tid; j < MA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense variant (default when W and a 64-bit accumulator table both fit in shared memory): the RED version spends its
+// time in ~2.1 M L2 atomics per step that collide on a few hundred hot rows.  Here every CTA accumulates its envs'
+// contributions into a shared-memory fixed-point table (integer adds: order independent => bit-reproducible), then the
+// tables are summed across CTAs with a dense reduce-scatter through L2:
+//   P[b][*] = CTA b's table  | grid barrier |  CTA b sums its slice of all P[*]  -> T  | grid barrier |  every CTA reads T.
+// ~28 MB of L2 traffic and two counter barriers per step instead of the atomics.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier_local(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (ld_acquire_u64(counter) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename R, int DOM, int AW, bool EXT>
+__global__ void __launch_bounds__(512, 1) tile_dense_kernel(const StepArgs a, const int k_steps, const TileArgs ta) {
+    using Dom = Domain<DOM>;
+    constexpr int D = Dom::D;
+    constexpr bool TDPRED = AW == 1;
+    const int tid = threadIdx.x, BLOCK = blockDim.x, G = gridDim.x, b = blockIdx.x, lane = tid & 31;
+    const int M = ta.tp.memory_mask + 1, MA = M * AW;
+    const int64_t N = a.n;
+    const int64_t per_cta = (N + G - 1) / G;
+    const int64_t base = (int64_t)b * per_cta;
+    const int64_t end = base + per_cta < N ? base + per_cta : N;
+    const int n_chunks = (int)((per_cta + BLOCK - 1) / BLOCK);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* Gs = reinterpret_cast<unsigned long long*>(smem_raw);   // [M][AW] fixed-point dW of this CTA, this step
+    R* Wsm = reinterpret_cast<R*>(Gs + MA);                                      // [M][AW]
+    for (int j = tid; j < MA; j += BLOCK) { Wsm[j] = static_cast<const R*>(a.W)[j]; Gs[j] = 0ull; }
+    __syncthreads();
+
+    auto evalQ = [&](const TileTab& tab, R* q) {
+#pragma unroll
+        for (int c = 0; c < AW; ++c) q[c] = (R)0;
+#pragma unroll
+        for (int j = 0; j < kMaxTilings; ++j) {
+            if (j < tab.n) {
+#pragma unroll
+                for (int c = 0; c < AW; ++c) q[c] += Wsm[tab.idx[j] * AW + c];  // activation 1.0
+            }
+        }
+    };
+    auto prep = [&](const double* st, TileTab& tb) { tile_prepare<Dom>(st, ta.tp, tb); };
+    const double inv_fx = 1.0 / ta.fx_scale;
+    unsigned long long* P = ta.G;                          // [G][MA]
+    unsigned long long* T = ta.G + (size_t)G * MA;         // [MA]
+    const int slice = (MA + G - 1) / G;                    // entries of T owned by one CTA
+
+    for (int step = 0; step < k_steps; ++step) {
+        const uint64_t t = a.t + (uint64_t)step;
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int64_t i = base + (int64_t)chunk * BLOCK + tid;
+            const bool active = i < end;
+            long long fx = 0;
+            int col = 0;
+            TileTab tab_s;
+            tab_s.n = 0;
+            if (active) {
+                const uint64_t g = (uint64_t)(a.env_offset + i);
+                double s[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) s[d] = EXT ? a.ext_from[i * D + d] : a.states[i * D + d];
+                TileTab tab_n;
+                CoreOut<R> o;
+                env_core<R, DOM, AW, EXT>(a, t, g, s, prep, evalQ, evalQ, tab_s, tab_n, false, o, EXT ? a.ext_actions[i] : 0,
+                                          EXT ? a.ext_rewards[i] : 0.0, EXT ? a.ext_term[i] != 0 : false,
+                                          EXT ? a.ext_to + i * D : nullptr);
+                if (a.td) static_cast<R*>(a.td)[i] = o.residual;
+                if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
+                fx = __double2ll_rn((double)o.coef * ta.fx_scale);
+                col = TDPRED ? 0 : o.act;
+                if (!EXT) {
+                    a.ep_steps[i] = env_bookkeeping<Dom>(a, t, i, g, s, a.ep_steps[i], o.terminated);
+                    a.actions[i] = o.act;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
+                }
+            }
+            // dW[row, a_t] += coef for every active row (activation 1.0).  When the whole warp hits the same entry (envs
+            // start in the same tiles) the warp adds once.
+#pragma unroll
+            for (int j = 0; j < kMaxTilings; ++j) {
+                if (j >= ta.tp.n_tilings) break;  // uniform
+                const int key = (active && j < tab_s.n) ? tab_s.idx[j] * AW + col : -1;
+                int same;
+                __match_all_sync(0xffffffffu, key, &same);
+                if (same) {
+                    if (key >= 0) {
+                        long long v = fx;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (lane == 0) atomicAdd(Gs + key, (unsigned long long)v);
+                    }
+                } else if (key >= 0) {
+                    atomicAdd(Gs + key, (unsigned long long)fx);
+                }
+            }
+        }
+        __syncthreads();
+        if (G > 1) {
+            // publish this CTA's table (and clear it for the next step)
+            unsigned long long* Pb = P + (size_t)b * MA;
+            for (int j = tid; j < MA; j += BLOCK) { __stcg(Pb + j, Gs[j]); Gs[j] = 0ull; }
+            grid_barrier_local(ta.barrier, (unsigned long long)(2 * step + 1) * (unsigned long long)G);
+            // reduce-scatter: this CTA sums entries [b*slice, (b+1)*slice) over all partials; warp per entry, lanes over CTAs
+            const int e0 = b * slice, e1 = e0 + slice < MA ? e0 + slice : MA;
+            for (int e = e0 + (tid >> 5); e < e1; e += BLOCK >> 5) {
+                long long v = 0;
+                for (int g2 = lane; g2 < G; g2 += 32) v += (long long)__ldcg(P + (size_t)g2 * MA + e);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) __stcg(T + e, (unsigned long long)v);
+            }
+            grid_barrier_local(ta.barrier, (unsigned long long)(2 * step + 2) * (unsigned long long)G);
+            for (int j = tid; j < MA; j += BLOCK) Wsm[j] += (R)((double)(long long)__ldcg(T + j) * inv_fx);
+        } else {
+            for (int j = tid; j < MA; j += BLOCK) { Wsm[j] += (R)((double)(long long)Gs[j] * inv_fx); Gs[j] = 0ull; }
+        }
         __syncthreads();
     }
     if (b == 0)

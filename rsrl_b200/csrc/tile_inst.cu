@@ -10,8 +10,9 @@ typedef RSRL_REAL R;
 
 template <int DOM, int AW, bool EXT>
 static cudaError_t tile_one(const StepArgs& a, int k_steps, const TileArgs& ta, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = tile_persistent_kernel<R, DOM, AW, EXT>;
-    static size_t configured = 0;
+    auto kern = ta.dense ? tile_dense_kernel<R, DOM, AW, EXT> : tile_persistent_kernel<R, DOM, AW, EXT>;
+    static size_t configured_v[2] = {0, 0};
+    size_t& configured = configured_v[ta.dense ? 1 : 0];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

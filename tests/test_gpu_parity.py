@@ -227,6 +227,7 @@ ALGOS = [
     ("qlearning_eps", dict(algo=abi.QLEARNING, policy=abi.EPSILON_GREEDY, epsilon=0.1)),
     ("sarsa_eps", dict(algo=abi.SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=0.01)),
     ("expected_sarsa_eps", dict(algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, lr=0.01)),
+    ("pal_eps", dict(algo=abi.PAL, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, gamma=0.95, lr=0.01)),  # control/td/pal.rs
     ("sarsa_lambda_replace", dict(algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99,
                                   trace_rule=abi.TRACE_REPLACE)),
     ("q_lambda_accumulate", dict(algo=abi.Q_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.002, gamma=0.99,
@@ -301,7 +302,7 @@ def test_engine_free_run_d4_domains(E, oracle, domain, order, algo):
 # ---------------------------------------------------------------------------------------------
 # dtype f32 (bench dtype): teacher-forced single steps within fp32 tolerance + short free run
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,kw", ALGOS[:4], ids=[a[0] for a in ALGOS[:4]])
+@pytest.mark.parametrize("name,kw", ALGOS[:5], ids=[a[0] for a in ALGOS[:5]])
 def test_engine_f32_teacher_forced(E, oracle, name, kw):
     """Each step starts from the same inputs on both sides (oracle state/weights copied from the device):
     next states within 1e-12 (f64 physics), TD errors within 1.2e-5 relative to the largest |TD error| / |weight|, weights within 1e-6 relative (fp32 features/Q),
@@ -598,7 +599,7 @@ def _f4tc_cfg(domain, n, algo, **kw):
     return abi.default_config(**base)
 
 
-@pytest.mark.parametrize("domain,n,algo", [(AC, 300, abi.EXPECTED_SARSA), (CP, 1000, abi.QLEARNING), (AC, 4113, abi.SARSA)])
+@pytest.mark.parametrize("domain,n,algo", [(AC, 300, abi.EXPECTED_SARSA), (CP, 1000, abi.QLEARNING), (AC, 4113, abi.SARSA), (AC, 777, abi.PAL)])
 def test_f4tc_single_step_matches_oracle(E, oracle, domain, n, algo):
     """n is ragged on purpose (not a multiple of the 128-env GEMM tile or the 32-env dW sub-tile)."""
     cfg = _f4tc_cfg(domain, n, algo)

@@ -218,3 +218,42 @@ def test_tile_coding_structure(oracle):
     assert len(base & set(oracle.tile_indices(cfg, far).tolist())) <= 1
     phi = oracle.project(cfg, [x])[0]
     assert phi.sum() == len(base) and set(np.nonzero(phi)[0].tolist()) == base
+
+
+def test_oracle_pal_matches_independent_restatement(oracle):
+    """control/td/pal.rs:35-59 restated in numpy (independent of the C oracle): residual = max(AL error, persistent
+    AL error) with the reference's literal bootstrap from nqs[a_star]; update error = alpha * residual."""
+    cfg = abi.default_config(algo=abi.PAL, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, gamma=0.95, lr=0.01, n_envs=64,
+                             dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[-0.4, 0.0], seed=2,
+                             record_td_error=1)
+    o = oracle.Engine(cfg)
+    W0 = np.random.default_rng(0).normal(size=(36, 3)) * 0.3
+    o.set_weights(W0)
+    s = o.states().copy()
+    o.step(1)
+    a, td = o.actions(), o.td_errors()
+    Q = oracle.evaluate(cfg, W0, s)
+    ns, r, term = oracle.domain_step(abi.MOUNTAIN_CAR, s, a)
+    NQ = oracle.evaluate(cfg, W0, ns)
+
+    def argmax_first(v):  # utils.rs:23-34
+        idx, x = 0, -1.7976931348623157e308
+        for j, y in enumerate(v):
+            if y - x > 1e-7:
+                idx, x = j, y
+        return idx
+
+    want, dW = [], np.zeros_like(W0)
+    phi = oracle.project(cfg, s)
+    for i in range(64):
+        if term[i]:
+            res = r[i] - Q[i, a[i]]
+        else:
+            a_star, na_star = argmax_first(Q[i]), argmax_first(NQ[i])
+            td_error = r[i] + 0.95 * NQ[i, a_star] - Q[i, a[i]]
+            al_error = td_error - 0.5 * (Q[i, a_star] - Q[i, a[i]])
+            res = max(al_error, td_error - 0.5 * (NQ[i, na_star] - NQ[i, a[i]]))
+        want.append(res)
+        dW[:, a[i]] += 0.01 * (0.5 * res) * phi[i]
+    assert np.abs(np.array(want) - td).max() < 1e-12
+    assert np.abs(o.weights() - (W0 + dW)).max() < 1e-12
