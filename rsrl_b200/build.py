@@ -47,6 +47,11 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    # The library is newer than every source: nothing to do, even when the object files did not travel with the tree
+    # (the GPU box receives the prebuilt .so without csrc/build/).
+    srcs = sorted({os.path.join(CSRC, u[1]) for u in _units()}) + [os.path.join(CSRC, h) for hs in EXTRA_DEPS.values() for h in hs]
+    if not force and not _stale(LIB, srcs + hdrs):
+        return LIB
     jobs = []
     for obj, src, defs in _units():
         o, s = os.path.join(OBJ, obj), os.path.join(CSRC, src)

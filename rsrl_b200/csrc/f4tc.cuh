@@ -545,8 +545,9 @@ __global__ void __launch_bounds__(128) f4tc_phys_kernel(const StepArgs a, const 
 // 2(q%2)..+1.  K index = (part, env): two units per sub-tile (real, imaginary), double-buffered: the generators publish
 // a unit (full barrier), the issuer queues its MMAs and commits them (done barrier) while the next unit is generated.
 // 3xTF32 in two MMAs per K step: A_hi x [B_hi; B_lo] (N = 2 NB: hi*hi and hi*lo land in separate column ranges) and
-// A_lo x B_hi (N = NB) — an SS-mode MMA costs >= 70 cycles for its A fetch whatever N is (tools/microbench), so
-// folding the third pass into a wider second operand saves a third of the tensor time.  The accumulator stays in TMEM
+// A_lo x B_hi (N = NB) — an SS-mode M = 128 MMA reads 4 KB of A from shared memory whatever N is (56 cycles at N = 96
+// against a 48-cycle tensor floor, tools/microbench), so folding the third pass into a wider second operand saves a
+// quarter of the tensor time and a third of the A traffic.  The accumulator stays in TMEM
 // for the whole kernel; the two column ranges are added in the epilogue.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW>

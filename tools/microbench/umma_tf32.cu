@@ -34,6 +34,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (TS mode): 128 lanes x K columns of 32-bit tf32 values
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -83,7 +97,7 @@ struct Params {
     const float* A;  // [128][64]
     const float* B;  // [N][64]
     float* D;        // [128][N]
-    int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad;
+    int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad, ts;
     long long* cycles;
     int* flags;
 };
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -130,6 +144,23 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (p.ts) {  // thread = row: A[row][0..63] hi -> columns 256.., lo -> columns 320..
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            float hi[8], lo[8];
+            for (int x = 0; x < 8; ++x) {
+                const float v = p.A[tid * K + k0 + x];
+                hi[x] = tf32_rna(v);
+                lo[x] = tf32_rna(v - hi[x]);
+            }
+            tmem_st8(lane_base + 256 + k0, hi);
+            tmem_st8(lane_base + 320 + k0, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -145,15 +176,37 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     long long t0 = 0, t1 = 0;
     bool ok = true;
     if (tid == 0) {
-        t0 = clock64();
-        for (int rep = 0; rep < p.reps; ++rep) {
-            for (int pass = 0; pass < p.passes; ++pass) {
+        // descriptors precomputed: the timed loop is MMA issue only (a single thread that also builds descriptors is
+        // issue-bound at ~110-140 cycles per MMA)
+        uint64_t adv[3][8], bdv[3][8];
+        uint32_t atm[3][8];
+        for (int pass = 0; pass < 3; ++pass)
+            for (int ks = 0; ks < 8; ++ks) {
                 const float* As = pass == 1 ? Alo : Ahi;
                 const float* Bs = pass == 2 ? Blo : Bhi;
-                for (int ks = 0; ks < K / 8; ++ks) {
-                    const uint64_t ad = make_desc(smem_u32(As) + ks * a_step, a_lbo, a_sbo);
-                    const uint64_t bd = make_desc(smem_u32(Bs) + ks * b_step, b_lbo, b_sbo);
-                    umma_tf32(tmem, ad, bd, idesc, (rep | pass | ks) != 0 ? 1u : 0u);
+                adv[pass][ks] = make_desc(smem_u32(As) + ks * a_step, a_lbo, a_sbo);
+                bdv[pass][ks] = make_desc(smem_u32(Bs) + ks * b_step, b_lbo, b_sbo);
+                atm[pass][ks] = tmem + (pass == 1 ? 320 : 256) + ks * 8;
+            }
+        t0 = clock64();
+        if (p.ts) {
+            for (int rep = 0; rep < p.reps; ++rep) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    if (pass < p.passes) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(tmem, atm[pass][ks], bdv[pass][ks], idesc, (rep | pass | ks) != 0 ? 1u : 0u);
+                    }
+                }
+            }
+        } else {
+            for (int rep = 0; rep < p.reps; ++rep) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    if (pass < p.passes) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) umma_tf32(tmem, adv[pass][ks], bdv[pass][ks], idesc, (rep | pass | ks) != 0 ? 1u : 0u);
+                    }
                 }
             }
         }
@@ -173,7 +226,7 @@ __global__ void __launch_bounds__(128) umma_test_kernel(Params p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 int main() {
@@ -191,20 +244,19 @@ int main() {
     cudaMemcpy(dB, hBfull.data(), hBfull.size() * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 
-    struct Case { const char* name; int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad; };
+    struct Case { const char* name; int N, passes, a_mn, b_mn, swap, swap_desc, reps, rna, pad, ts; };
     const Case cases[] = {
-        {"K-major N=192 3xTF32 (correctness)", 192, 3, 0, 0, 0, 0, 1, 1, 0},
-        {"K-major N=96 3xTF32 padded LBO+16 (correctness)", 96, 3, 0, 0, 0, 0, 1, 1, 16},
-        {"K-major N=192 timing reps=64", 192, 3, 0, 0, 0, 0, 64, 1, 0},
-        {"K-major N=192 timing reps=64 padded", 192, 3, 0, 0, 0, 0, 64, 1, 16},
-        {"K-major N=96 timing reps=64", 96, 3, 0, 0, 0, 0, 64, 1, 0},
-        {"K-major N=96 timing reps=64 padded LBO+16", 96, 3, 0, 0, 0, 0, 64, 1, 16},
-        {"K-major N=96 timing reps=64 swapped layout (K chunks adjacent)", 96, 3, 0, 0, 1, 0, 64, 1, 0},
-        {"K-major N=64 timing reps=64", 64, 3, 0, 0, 0, 0, 64, 1, 0},
-        {"K-major N=256 timing reps=64", 256, 3, 0, 0, 0, 0, 64, 1, 0},
+        {"SS K-major N=192 3xTF32 (correctness)", 192, 3, 0, 0, 0, 0, 1, 1, 0, 0},
+        {"TS (A in TMEM) N=192 3xTF32 (correctness)", 192, 3, 0, 0, 0, 0, 1, 1, 0, 1},
+        {"TS N=96 3xTF32 padded B (correctness)", 96, 3, 0, 0, 0, 0, 1, 1, 16, 1},
+        {"SS N=192 timing reps=64", 192, 3, 0, 0, 0, 0, 64, 1, 0, 0},
+        {"TS N=192 timing reps=64", 192, 3, 0, 0, 0, 0, 64, 1, 0, 1},
+        {"SS N=96 timing reps=64", 96, 3, 0, 0, 0, 0, 64, 1, 0, 0},
+        {"TS N=96 timing reps=64", 96, 3, 0, 0, 0, 0, 64, 1, 0, 1},
+        {"TS N=64 timing reps=64", 64, 3, 0, 0, 0, 0, 64, 1, 0, 1},
     };
     for (const Case& c : cases) {
-        Params p{dA, dB, dD, c.N, c.passes, c.a_mn, c.b_mn, c.swap, c.swap_desc, c.reps, c.rna, c.pad, dC, dF};
+        Params p{dA, dB, dD, c.N, c.passes, c.a_mn, c.b_mn, c.swap, c.swap_desc, c.reps, c.rna, c.pad, c.ts, dC, dF};
         cudaMemset(dF, 0, 4);
         cudaMemset(dD, 0, M * 256 * 4);
         const size_t smem = (size_t)(2 * M * K + 2 * c.N * K) * 4 + 1024 + 4 * 16 * 64;
