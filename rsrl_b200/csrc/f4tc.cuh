@@ -235,6 +235,24 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
                 const int first = blockIdx.x * 2 + g2;
                 units[g2] = first < n_tiles ? ((n_tiles - first - 1) / ((int)gridDim.x * 2) + 1) * 8 : 0;  // 2 parts x 4 K quarters per tile
             }
+            // descriptors are loop invariant: built once (a thread that rebuilds them per MMA is issue bound, tools/microbench)
+            uint64_t adesc[2][2][2][2], bdesc[2][4][2];  // A: [group][buffer][hi, lo][K step]; B: [hi, lo][K quarter][K step]
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                            adesc[g2][b][hl][ks] = tc::make_desc(tc::smem_u32(Abase + (g2 * 4 + b * 2 + hl) * SM::UNIT_FLOATS) + ks * 2 * A_LBO, A_LBO, SBO);
+#pragma unroll
+            for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        bdesc[hl][kq][ks] = tc::make_desc(tc::smem_u32(hl ? Blo : Bhi) + (uint32_t)(kq * 4 + ks * 2) * B_LBO, B_LBO, SBO);
             int spins = 0;
             long long t_issue = 0, t_idle = 0, t_last = clock64();
             while (cnt[0] < units[0] || cnt[1] < units[1]) {
@@ -247,17 +265,18 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
                         { const long long now = clock64(); t_idle += now - t_last; t_last = now; }
                         tc::fence_after_sync();
                         const int kq = cnt[g2] & 3;
-                        const float* Ah = Abase + (g2 * 4 + b * 2) * SM::UNIT_FLOATS;
-                        const float* Al = Ah + SM::UNIT_FLOATS;
                         const uint32_t acc2 = tmem_slot + (uint32_t)(g2 * 256);
+                        // 3xTF32: hi*hi + lo*hi + hi*lo; kq, b are runtime: select among the precomputed descriptors
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t abase = tc::smem_u32(pass == 1 ? Al : Ah);
-                            const uint32_t bbase = tc::smem_u32(pass == 2 ? Blo : Bhi) + (uint32_t)kq * 4u * B_LBO;
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks)
-                                tc::umma_tf32(acc2, tc::make_desc(abase + ks * 2 * A_LBO, A_LBO, SBO), tc::make_desc(bbase + ks * 2 * B_LBO, B_LBO, SBO),
-                                              IDESC, (kq | pass | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const int ahl = pass == 1 ? 1 : 0, bhl = pass == 2 ? 1 : 0;
+                                const uint64_t ad = b ? adesc[g2][1][ahl][ks] : adesc[g2][0][ahl][ks];
+                                const uint64_t b01 = (kq & 1) ? bdesc[bhl][1][ks] : bdesc[bhl][0][ks];
+                                const uint64_t b23 = (kq & 1) ? bdesc[bhl][3][ks] : bdesc[bhl][2][ks];
+                                tc::umma_tf32(acc2, ad, (kq & 2) ? b23 : b01, IDESC, (kq | pass | ks) != 0 ? 1u : 0u);
+                            }
                         }
                         tc::umma_commit(tc::smem_u32(&bars[g2][b]));
                         { const long long now = clock64(); t_issue += now - t_last; t_last = now; }
