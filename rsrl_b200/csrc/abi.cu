@@ -493,14 +493,19 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         e->pgrid = (int)((e->N + 127) / 128);
         if (e->pgrid > sms) e->pgrid = sms;
         const int64_t per_cta = (e->N + e->pgrid - 1) / e->pgrid;
-        e->pblock = (int)((per_cta + 31) / 32 * 32);
-        if (e->pblock > 512) e->pblock = 512;
+        // dense kernel: up to 1024 threads per CTA (64 registers: the f64 RK4 spills ~700 B to L1, but 32 warps hide its latencies:
+        // 61.9 us/step vs 70.5 at 512 threads on cfg3), envs split evenly over the chunks; RSRL_B200_TILE_BLOCK caps the block size
+        const int max_block = getenv("RSRL_B200_TILE_BLOCK") ? atoi(getenv("RSRL_B200_TILE_BLOCK")) : 1024;
+        const int64_t chunks = (per_cta + max_block - 1) / max_block;
+        e->pblock = (int)(((per_cta + chunks - 1) / chunks + 31) / 32 * 32);
+        if (e->pblock > max_block) e->pblock = max_block;
         if (e->pblock < 64) e->pblock = 64;
         e->psmem = (size_t)e->FA * e->rsz;
         // dense variant: W + a 64-bit accumulator table per CTA in shared memory (RSRL_B200_TILE_DENSE=0 keeps the RED-atomics kernel)
         const size_t dense_smem = (size_t)e->FA * (e->rsz + sizeof(unsigned long long));
         e->targs.dense = dense_smem <= 200 * 1024 && !(getenv("RSRL_B200_TILE_DENSE") && atoi(getenv("RSRL_B200_TILE_DENSE")) == 0);
         if (e->targs.dense) e->psmem = dense_smem;
+        else if (e->pblock > 512) e->pblock = 512;  // tile_persistent_kernel: __launch_bounds__(512, 1)
         e->grid = 1; e->block = 64; e->smem = 0;
     } else {
         choose_launch(e);

@@ -119,7 +119,7 @@ __device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
             for (int i = 0; i < 4; ++i) {
                 k[i] = dmul(k[i], dx);
                 sum[i] = st == 0 ? k[i] : dadd(sum[i], mid ? dmul(2.0, k[i]) : k[i]);
-                tmp[i] = dadd(y[i], st < 2 ? ddiv(k[i], 2.0) : k[i]);
+                tmp[i] = dadd(y[i], st < 2 ? dmul(k[i], 0.5) : k[i]);  // k/2.0 == k*0.5 bit for bit
             }
         }
 #pragma unroll
@@ -129,10 +129,10 @@ __device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
     double k1[4], k2[4], k3[4], k4[4], tmp[4];
     f(y, k1);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { k1[i] = dmul(k1[i], dx); tmp[i] = dadd(y[i], ddiv(k1[i], 2.0)); }
+    for (int i = 0; i < 4; ++i) { k1[i] = dmul(k1[i], dx); tmp[i] = dadd(y[i], dmul(k1[i], 0.5)); }  // k/2.0 == k*0.5 bit for bit
     f(tmp, k2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { k2[i] = dmul(k2[i], dx); tmp[i] = dadd(y[i], ddiv(k2[i], 2.0)); }
+    for (int i = 0; i < 4; ++i) { k2[i] = dmul(k2[i], dx); tmp[i] = dadd(y[i], dmul(k2[i], 0.5)); }
     f(tmp, k3);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { k3[i] = dmul(k3[i], dx); tmp[i] = dadd(y[i], k3[i]); }

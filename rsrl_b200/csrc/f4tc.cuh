@@ -174,7 +174,7 @@ struct F4tcEnvSmem {
 };
 
 template <int DOM, int PHASE, bool EXT>
-__global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const F4Args fa, int n_tiles, int stagger, unsigned idle_ns) {
+__global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const F4Args fa, int n_tiles) {
     using Dom = Domain<DOM>;
     constexpr int D = 4, P = 7, AW = Dom::A;
     using SM = F4tcEnvSmem<AW>;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
                     }
                 }
                 if (!progressed) {
-                    __nanosleep(idle_ns);  // the poll loop shares a scheduler with two group warps: do not steal their issue slots
+                    __nanosleep(50);  // the poll loop shares a scheduler with two group warps: do not steal their issue slots
                     if (++spins > (1 << 24)) { atomicExch(fault, 1); break; }
                 }
             }
@@ -420,10 +420,6 @@ __global__ void __launch_bounds__(288, 1) f4tc_q_kernel(const StepArgs a, const 
         }
     };
 
-    // The two groups run identical work: started together they drain the tensor pipe at the same moments (both
-    // contracting, both building tables) and it idles half of the time.  Group 1 starts half a part late.
-    if (grp == 1 && stagger > 0) { const long long t0 = clock64(); while (clock64() - t0 < stagger) {} }
-    (void)idle_ns;
     for (int tile = blockIdx.x * 2 + grp; tile < n_tiles; tile += gridDim.x * 2) {
         const int64_t i = (int64_t)tile * 128 + gt;
         const bool active = i < a.n;

@@ -15,9 +15,7 @@ static cudaError_t q_one(const StepArgs& a, const F4Args& fa, int n_tiles, int g
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    static const int stagger = getenv("RSRL_B200_F4TC_STAGGER") ? atoi(getenv("RSRL_B200_F4TC_STAGGER")) : 2500;  // cycles (tuning aid)
-    static const unsigned idle_ns = getenv("RSRL_B200_F4TC_IDLE_NS") ? (unsigned)atoi(getenv("RSRL_B200_F4TC_IDLE_NS")) : 50u;
-    kern<<<grid, 288, smem, st>>>(a, fa, n_tiles, stagger, idle_ns);
+    kern<<<grid, 288, smem, st>>>(a, fa, n_tiles);
     return cudaGetLastError();
 }
 

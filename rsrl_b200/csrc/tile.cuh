@@ -139,8 +139,8 @@ __device__ __forceinline__ void grid_barrier_local(unsigned long long* counter, 
     __syncthreads();
 }
 
-template <typename R, int DOM, int AW, bool EXT>
-__global__ void __launch_bounds__(512, 1) tile_dense_kernel(const StepArgs a, const int k_steps, const TileArgs ta) {
+template <typename R, int DOM, int AW, bool EXT, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, const int k_steps, const TileArgs ta) {
     using Dom = Domain<DOM>;
     constexpr int D = Dom::D;
     constexpr bool TDPRED = AW == 1;
