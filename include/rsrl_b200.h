@@ -66,8 +66,10 @@ typedef enum rsrl_algo {
     RSRL_SARSA_LAMBDA = 3, RSRL_Q_LAMBDA = 4, RSRL_TD_LAMBDA = 5, RSRL_TD0 = 6,
     RSRL_PAL = 7 /* persistent advantage learning, control/td/pal.rs:35-59 (update error = alpha * residual) */
 } rsrl_algo_t;
-/* rsrl/src/policies/{greedy,epsilon_greedy,random}.rs */
-typedef enum rsrl_policy { RSRL_GREEDY = 0, RSRL_EPSILON_GREEDY = 1, RSRL_RANDOM = 2 } rsrl_policy_t;
+/* rsrl/src/policies/{greedy,epsilon_greedy,random,softmax}.rs.  RSRL_SOFTMAX (= Gibbs, softmax.rs:38): probabilities
+ * softmax_stable(Q(s), tau) (softmax.rs:15-36), sample by inverse CDF (policies/mod.rs:46-61), mode = argmax_first of the
+ * probabilities (softmax.rs:141); its temperature tau travels in the `epsilon` field / argument. */
+typedef enum rsrl_policy { RSRL_GREEDY = 0, RSRL_EPSILON_GREEDY = 1, RSRL_RANDOM = 2, RSRL_SOFTMAX = 3 } rsrl_policy_t;
 /* rsrl/src/traces.rs:196-240  Accumulate / Saturate ("replacing") / Dutch */
 typedef enum rsrl_trace_rule { RSRL_TRACE_ACCUMULATE = 0, RSRL_TRACE_REPLACE = 1, RSRL_TRACE_DUTCH = 2 } rsrl_trace_rule_t;
 /* SHARED: one agent learns from N envs (W replicated per GPU, dW summed);
@@ -107,7 +109,7 @@ typedef struct rsrl_config {
     double   alpha;             /* agent step size: ExpectedSARSA (expected_sarsa.rs:64), PAL (pal.rs:49-57), lambda agents */
     double   gamma;
     double   lambda;
-    double   epsilon;
+    double   epsilon;           /* EpsilonGreedy: epsilon; Softmax: temperature tau (|tau| >= 1e-7, softmax.rs:61-64) */
     double   init_lo[RSRL_MAX_DIM];
     double   init_hi[RSRL_MAX_DIM];
 } rsrl_config_t;
@@ -159,7 +161,7 @@ int rsrl_engine_get_stats(rsrl_engine_t* e, rsrl_stats_t* out);
 /* per-env episode bookkeeping: episodes finished, length of the last finished episode,
  * rolling hash h = h * 1000003 + len over all finished episode lengths (bit-exact step-count check) */
 int rsrl_engine_get_env_stats(rsrl_engine_t* e, int32_t* n_episodes, int32_t* last_len, uint64_t* len_hash);
-int rsrl_engine_set_epsilon(rsrl_engine_t* e, double epsilon);  /* examples/sarsa_lambda.rs:68 decays it per episode */
+int rsrl_engine_set_epsilon(rsrl_engine_t* e, double epsilon);  /* examples/sarsa_lambda.rs:68 decays it per episode (Softmax: tau) */
 
 /* ---- engine, trait-level (un-fused) entry points on the engine's weights ---- */
 /* Function<(S,)>::evaluate for VectorLFA (fa/linear.rs:303-311): q_out N x A */

@@ -181,6 +181,12 @@ class Greedy {
 struct EpsilonGreedy : Greedy {
     EpsilonGreedy(std::shared_ptr<LFA> q, double epsilon) : Greedy(std::move(q), RSRL_EPSILON_GREEDY, epsilon) {}
 };
+// rsrl/src/policies/softmax.rs:52-69 (Gibbs = Softmax); the temperature travels in the config's epsilon field
+struct Softmax : Greedy {
+    Softmax(std::shared_ptr<LFA> q, double tau) : Greedy(std::move(q), RSRL_SOFTMAX, tau) {}
+    static Softmax standard(std::shared_ptr<LFA> q) { return Softmax(std::move(q), 1.0); }
+};
+using Gibbs = Softmax;
 
 // ---- control::td ----
 struct Response { double error; };  // q_learning.rs:17-20

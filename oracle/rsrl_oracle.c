@@ -378,8 +378,17 @@ enum { STREAM_INIT = 0, STREAM_BEHAVIOUR = 1, STREAM_TARGET = 2 };
 /* policies                                                                    */
 /* ------------------------------------------------------------------------- */
 /* Greedy::evaluate (greedy.rs:30-44), EpsilonGreedy::evaluate (epsilon_greedy.rs:38-45), Random (random.rs) */
+/* softmax.rs:15-36 softmax_stable */
+static void orc_softmax(const double* q, int n, double tau, double* p) {
+    double c = NAN, z = 0.0;
+    for (int i = 0; i < n; ++i) c = fmax(c, q[i]);            /* fold(f64::NAN, f64::max) */
+    for (int i = 0; i < n; ++i) { p[i] = exp((q[i] - c) / tau); z += p[i]; }
+    for (int i = 0; i < n; ++i) p[i] = fmin(p[i] / z, DBL_MAX);
+}
+
 void orc_policy_probs(int policy, double epsilon, const double* q, int n, double* p) {
     int ixs[16];
+    if (policy == RSRL_SOFTMAX) { orc_softmax(q, n, epsilon, p); return; } /* epsilon carries tau */
     if (policy == RSRL_RANDOM) { for (int i = 0; i < n; ++i) p[i] = 1.0 / (double)n; return; }
     for (int i = 0; i < n; ++i) p[i] = 0.0;
     int cnt = orc_argmaxima(q, n, ixs, NULL);
@@ -396,6 +405,13 @@ void orc_policy_probs(int policy, double epsilon, const double* q, int n, double
  * rnd[2] -> SliceRandom::choose among the maxima (utils.rs:70-76, only consulted on ties). */
 int orc_policy_sample(int policy, double epsilon, const double* q, int n, const uint32_t rnd[4], int* nonfinite) {
     int ixs[16];
+    if (policy == RSRL_SOFTMAX) { /* softmax.rs:137-139 -> policies/mod.rs:46-61: r = gen::<f64>() (53 bits: rnd[0] high, rnd[1] low) */
+        double p[16], cum = 0.0;
+        double r = (double)((((uint64_t)rnd[0] << 32) | (uint64_t)rnd[1]) >> 11) * (1.0 / 9007199254740992.0);
+        orc_softmax(q, n, epsilon, p);
+        for (int i = 0; i < n; ++i) { cum = cum + p[i]; if (cum > r) return i; }
+        return n - 1;
+    }
     int explore = policy == RSRL_RANDOM;
     if (policy == RSRL_EPSILON_GREEDY)
         explore = epsilon >= 1.0 || rnd[0] < (uint32_t)(epsilon * 4294967296.0);

@@ -13,7 +13,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ENONFINITE, ECOMM, ENODEVICE = 0, -1, -
 MOUNTAIN_CAR, CART_POLE, ACROBOT = 0, 1, 2
 FOURIER, POLYNOMIAL, TILE_CODING = 0, 1, 2
 QLEARNING, SARSA, EXPECTED_SARSA, SARSA_LAMBDA, Q_LAMBDA, TD_LAMBDA, TD0, PAL = range(8)
-GREEDY, EPSILON_GREEDY, RANDOM = 0, 1, 2
+GREEDY, EPSILON_GREEDY, RANDOM, SOFTMAX = 0, 1, 2, 3
 TRACE_ACCUMULATE, TRACE_REPLACE, TRACE_DUTCH = 0, 1, 2
 SHARED, PER_ENV = 0, 1
 SCALE_SUM, SCALE_MEAN = 0, 1

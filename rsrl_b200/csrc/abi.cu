@@ -65,12 +65,14 @@ static int validate(const rsrl_config_t* c) {
     if (c->domain < 0 || c->domain > 2) return fail(RSRL_EINVAL, "unknown domain");
     if (c->basis < 0 || c->basis > 2) return fail(RSRL_EINVAL, "unknown basis");
     if (c->algo < 0 || c->algo > RSRL_PAL) return fail(RSRL_EINVAL, "unknown algo");
-    if (c->policy < 0 || c->policy > 2) return fail(RSRL_EINVAL, "unknown policy");
+    if (c->policy < 0 || c->policy > RSRL_SOFTMAX) return fail(RSRL_EINVAL, "unknown policy");
     if (c->dtype != RSRL_F32 && c->dtype != RSRL_F64) return fail(RSRL_EINVAL, "unknown dtype");
     if (c->weight_mode != RSRL_SHARED && c->weight_mode != RSRL_PER_ENV) return fail(RSRL_EINVAL, "unknown weight_mode");
     if (c->n_envs <= 0) return fail(RSRL_EINVAL, "n_envs must be > 0");
     if (c->env_offset < 0 || c->env_offset + c->n_envs > 0xFFFFFFFFll) return fail(RSRL_EINVAL, "global env ids must fit 32 bits");
-    if (!(c->epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
+    if (c->policy == RSRL_SOFTMAX) {
+        if (!(c->epsilon <= -1e-7 || c->epsilon >= 1e-7)) return fail(RSRL_EINVAL, "Softmax: the temperature tau (epsilon field) must be non-zero (softmax.rs:61-64)");
+    } else if (!(c->epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
     if (c->basis != RSRL_TILE_CODING && (c->basis_order < 1 || c->basis_order > 7)) return fail(RSRL_EINVAL, "basis_order must be in 1..7");
     if (c->basis == RSRL_TILE_CODING) {
         if (c->n_tilings < 1 || c->n_tilings > kMaxTilings) return fail(RSRL_EINVAL, "n_tilings must be in 1..16");
@@ -103,6 +105,7 @@ static BasisKey key_of(const rsrl_config_t* c) {
 static PolicyParams policy_of(int policy, double eps, uint64_t seed) {
     PolicyParams p;
     p.policy = policy;
+    p.tau = eps;
     p.eps_always = eps >= 1.0;
     p.eps_thresh = p.eps_always ? 0xFFFFFFFFu : (uint32_t)(eps * 4294967296.0);
     p.seed = seed;
@@ -819,7 +822,8 @@ int rsrl_engine_get_env_stats(rsrl_engine_t* e, int32_t* n_episodes, int32_t* la
 
 int rsrl_engine_set_epsilon(rsrl_engine_t* e, double epsilon) {
     if (!e) return fail(RSRL_EINVAL, "null engine");
-    if (!(epsilon >= 0.0)) return fail(RSRL_EINVAL, "epsilon must be >= 0");
+    if (e->cfg.policy == RSRL_SOFTMAX ? !(epsilon <= -1e-7 || epsilon >= 1e-7) : !(epsilon >= 0.0))
+        return fail(RSRL_EINVAL, "epsilon must be >= 0 (Softmax: tau must be non-zero)");
     e->epsilon = epsilon;
     return RSRL_OK;
 }
@@ -1117,7 +1121,8 @@ extern "C" {
 static int policy_call(int mode, int32_t policy, double eps, uint64_t seed, uint64_t draw, int64_t env_offset, int64_t n,
                        int32_t A, const double* q, int32_t* act_out, double* probs_out) {
     if (n <= 0 || !q || A < 1 || A > 8) return fail(RSRL_EINVAL, "bad argument (1 <= n_actions <= 8)");
-    if (policy < 0 || policy > 2 || !(eps >= 0.0)) return fail(RSRL_EINVAL, "bad policy / epsilon");
+    if (policy < 0 || policy > RSRL_SOFTMAX || (policy == RSRL_SOFTMAX ? !(eps <= -1e-7 || eps >= 1e-7) : !(eps >= 0.0)))
+        return fail(RSRL_EINVAL, "bad policy / epsilon (Softmax: tau must be non-zero)");
     int rc = need_device();
     if (rc) return rc;
     DevBuf dq, dout, dc;

@@ -44,6 +44,9 @@ template <> struct RealOps<float> {
     __device__ __forceinline__ static float abs(float a) { return fabsf(a); }
     __device__ __forceinline__ static float lowest() { return -3.402823466e+38f; }  // magnitude only matters vs 1e-7
     __device__ __forceinline__ static float clamp1(float x) { return fmaxf(-1.0f, fminf(1.0f, x)); }
+    __device__ __forceinline__ static float exp(float x) { return expf(x); }
+    __device__ __forceinline__ static float max_nan(float a, float b) { return fmaxf(a, b); }  // f64::max: drops NaN
+    __device__ __forceinline__ static float min_max(float x) { return fminf(x, 3.402823466e+38f); }
 };
 template <> struct RealOps<double> {
     __device__ __forceinline__ static void sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
@@ -52,6 +55,9 @@ template <> struct RealOps<double> {
     __device__ __forceinline__ static double abs(double a) { return fabs(a); }
     __device__ __forceinline__ static double lowest() { return -1.7976931348623157e+308; }  // f64::MIN
     __device__ __forceinline__ static double clamp1(double x) { return fmax(-1.0, fmin(1.0, x)); }
+    __device__ __forceinline__ static double exp(double x) { return ::exp(x); }
+    __device__ __forceinline__ static double max_nan(double a, double b) { return fmax(a, b); }
+    __device__ __forceinline__ static double min_max(double x) { return fmin(x, 1.7976931348623157e+308); }
 };
 
 // ---------------------------------------------------------------------------
@@ -473,13 +479,43 @@ struct PolicyParams {
     uint32_t eps_thresh;  // floor(eps * 2^32)
     int eps_always;       // eps >= 1 (rand's gen_bool(1.0) is true without drawing)
     uint64_t seed;
+    double tau;           // Softmax temperature (the config's `epsilon` field)
 };
+
+// softmax.rs:15-36 softmax_stable: c = fold(NAN, f64::max); v_i = exp((q_i - c) / tau); p_i = min(v_i / sum v, MAX)
+template <typename R, int A>
+__device__ __forceinline__ void softmax_probs(R tau, const R* q, R* p) {
+    using O = RealOps<R>;
+    R c = q[0];
+#pragma unroll
+    for (int i = 1; i < A; ++i) c = O::max_nan(c, q[i]);
+    R z = (R)0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) { p[i] = O::exp((q[i] - c) / tau); z += p[i]; }
+#pragma unroll
+    for (int i = 0; i < A; ++i) p[i] = O::min_max(p[i] / z);
+}
 
 // Policy::sample — greedy.rs:77-81 (argmax_choose_rng: RNG only on ties), epsilon_greedy.rs:74-80,
 // random.rs:43-45.  rnd.x -> gen_bool(eps), rnd.y -> Uniform(0, A), rnd.z -> choose among maxima.
 template <typename R, int A>
 __device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, uint64_t g, uint64_t draw,
                                              uint32_t stream, bool& nonfinite) {
+    if (p.policy == RSRL_SOFTMAX) {
+        // policies/mod.rs:46-61 sample_probs_with_rng: r = rng.gen::<f64>() (53 bits: rnd.x high, rnd.y low);
+        // first index whose running sum exceeds r, else the last
+        R pr[A];
+        softmax_probs<R, A>((R)p.tau, q, pr);
+        const uint4 rn = draw4(p.seed, g, draw, stream);
+        const double r = (double)((((unsigned long long)rn.x << 32) | (unsigned long long)rn.y) >> 11) * (1.0 / 9007199254740992.0);
+        R cum = (R)0;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            cum = cum + pr[i];
+            if ((double)cum > r) return i;
+        }
+        return A - 1;
+    }
     if (p.policy != RSRL_GREEDY) {
         const uint4 r = draw4(p.seed, g, draw, stream);
         const bool explore = p.policy == RSRL_RANDOM || p.eps_always || r.x < p.eps_thresh;
@@ -501,6 +537,7 @@ __device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, 
 // Function<(S,)>::evaluate of the policy (greedy.rs:30-44, epsilon_greedy.rs:38-45)
 template <typename R, int A>
 __device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p) {
+    if (policy == RSRL_SOFTMAX) { softmax_probs<R, A>(eps, q, p); return; }  // eps carries tau
     if (policy == RSRL_RANDOM) {
 #pragma unroll
         for (int i = 0; i < A; ++i) p[i] = (R)1 / (R)A;
@@ -516,6 +553,18 @@ __device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p
 #pragma unroll
         for (int i = 0; i < A; ++i) p[i] = pr + p[i] * ((R)1 - eps);
     }
+}
+
+// Policy::mode — greedy.rs:83 find_max; softmax.rs:141 argmax_first over the probabilities
+template <typename R, int A>
+__device__ __forceinline__ int policy_mode(int policy, R tau, const R* q) {
+    if (policy == RSRL_SOFTMAX) {
+        R p[A];
+        softmax_probs<R, A>(tau, q, p);
+        return argmax_first<R, A>(p);
+    }
+    R mx;
+    return find_max<R, A>(q, mx);
 }
 
 // traces.rs:196-240

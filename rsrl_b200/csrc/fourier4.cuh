@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(128) f4_eval_kernel(int mode, int64_t n, const
         if (nf) atomicExch(&counters->nonfinite, 1);
     } else if (mode == 3) {
         R mx;
-        act_out[i] = find_max<R, AW>(q, mx);
+        (void)mx;
+        act_out[i] = policy_mode<R, AW>(pol.policy, (R)pol.tau, q);
     }
 }
 

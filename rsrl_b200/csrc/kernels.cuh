@@ -398,7 +398,8 @@ __global__ void basis_eval_kernel(int mode, int64_t n, const double* __restrict_
         if (nf) atomicExch(&counters->nonfinite, 1);
     } else {
         R mx;
-        act_out[i] = find_max<R, AW>(q, mx);
+        (void)mx;
+        act_out[i] = policy_mode<R, AW>(pol.policy, (R)pol.tau, q);
     }
 }
 

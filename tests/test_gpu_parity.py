@@ -227,6 +227,8 @@ ALGOS = [
     ("qlearning_eps", dict(algo=abi.QLEARNING, policy=abi.EPSILON_GREEDY, epsilon=0.1)),
     ("sarsa_eps", dict(algo=abi.SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=0.01)),
     ("expected_sarsa_eps", dict(algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, lr=0.01)),
+    ("sarsa_softmax", dict(algo=abi.SARSA, policy=abi.SOFTMAX, epsilon=0.7, gamma=0.95, lr=0.01)),  # policies/softmax.rs (epsilon field = tau)
+    ("expected_sarsa_softmax", dict(algo=abi.EXPECTED_SARSA, policy=abi.SOFTMAX, epsilon=2.0, alpha=0.5, lr=0.01)),
     ("pal_eps", dict(algo=abi.PAL, policy=abi.EPSILON_GREEDY, epsilon=0.1, alpha=0.5, gamma=0.95, lr=0.01)),  # control/td/pal.rs
     ("sarsa_lambda_replace", dict(algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99,
                                   trace_rule=abi.TRACE_REPLACE)),
@@ -302,7 +304,7 @@ def test_engine_free_run_d4_domains(E, oracle, domain, order, algo):
 # ---------------------------------------------------------------------------------------------
 # dtype f32 (bench dtype): teacher-forced single steps within fp32 tolerance + short free run
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,kw", ALGOS[:5], ids=[a[0] for a in ALGOS[:5]])
+@pytest.mark.parametrize("name,kw", ALGOS[:4] + ALGOS[6:7], ids=[a[0] for a in ALGOS[:4] + ALGOS[6:7]])
 def test_engine_f32_teacher_forced(E, oracle, name, kw):
     """Each step starts from the same inputs on both sides (oracle state/weights copied from the device):
     next states within 1e-12 (f64 physics), TD errors within 1.2e-5 relative to the largest |TD error| / |weight|, weights within 1e-6 relative (fp32 features/Q),
@@ -668,6 +670,29 @@ def test_f4tc_handle_entry_point(E, oracle):
         assert np.abs(td_e - td_o).max() < 1.2e-5 * max(1.0, np.abs(td_o).max())
         assert np.abs(e.weights() - o.weights()).max() < 1e-6 * np.abs(o.weights()).max()
         assert np.abs(e.evaluate(s) - oracle.evaluate(cfg, o.weights(), s)).max() < 2e-5 * 10 * 64
+
+
+def test_softmax_policy_entry_points(E, oracle):
+    """Stateless Policy::sample / evaluate for Softmax on explicit Q vectors + Policy::mode through an engine."""
+    rng = np.random.default_rng(8)
+    q = rng.normal(size=(3000, 3)) * 2
+    q[:5] = [[0, 1, 0], [5, 5, 5], [700, 710, 705], [-1e3, 0, 1e-3], [1e-9, 0, 0]]
+    for tau in (1.0, 0.25):
+        want_p = np.array([oracle.policy_probs(abi.SOFTMAX, tau, qi) for qi in q])
+        assert np.abs(E.policy_probs(abi.SOFTMAX, tau, q) - want_p).max() < 1e-14
+        got = E.policy_sample(abi.SOFTMAX, tau, seed=21, draw=6, env_offset=100, q=q)
+        want = oracle.policy_sample_batch(abi.SOFTMAX, tau, 21, 6, 100, q)
+        assert (got == want).all()
+    cfg = abi.default_config(policy=abi.SOFTMAX, epsilon=0.5, dtype=abi.F64, n_envs=64)
+    s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(64, 2))
+    W = rng.normal(size=(36, 3))
+    with E.Engine(cfg) as e:
+        e.set_weights(W)
+        Q = oracle.evaluate(cfg, W, s)
+        P = np.array([oracle.policy_probs(abi.SOFTMAX, 0.5, qi) for qi in Q])
+        want_mode = [oracle.argmax_first(p)[0] for p in P]                 # softmax.rs:141
+        assert (e.mode(s) == np.array(want_mode)).all()
+        assert (e.sample(s, draw=3) == oracle.policy_sample_batch(abi.SOFTMAX, 0.5, cfg.seed, 3, 0, Q)).all()
 
 
 # ---------------------------------------------------------------------------------------------

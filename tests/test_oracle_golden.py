@@ -257,3 +257,30 @@ def test_oracle_pal_matches_independent_restatement(oracle):
         dW[:, a[i]] += 0.01 * (0.5 * res) * phi[i]
     assert np.abs(np.array(want) - td).max() < 1e-12
     assert np.abs(o.weights() - (W0 + dW)).max() < 1e-12
+
+
+# Softmax / Gibbs (policies/softmax.rs): probability golden values of test_probabilites_1 (:253-269), test_1d (:239-246),
+# the expected sampling frequencies of test_2d (:248-262), inverse-CDF sampling (policies/mod.rs:46-61)
+def test_softmax_probabilities_golden(oracle):
+    e = np.e
+    assert np.abs(oracle.policy_probs(abi.SOFTMAX, 1.0, [0.0, 1.0]) - [1 / (1 + e), e / (1 + e)]).max() < 1e-15
+    assert np.abs(oracle.policy_probs(abi.SOFTMAX, 1.0, [0.0, 2.0]) - [1 / (1 + e * e), e * e / (1 + e * e)]).max() < 1e-15
+    p = oracle.policy_probs(abi.SOFTMAX, 0.5, [700.0, 710.0, 705.0])      # softmax_stable: no overflow
+    assert np.isfinite(p).all() and abs(p.sum() - 1) < 1e-15 and p.argmax() == 1
+    for i in range(1, 100):                                              # test_1d
+        assert oracle.policy_sample(abi.SOFTMAX, 1.0, [float(i)], [i * 7919, i, 0, 0])[0] == 0
+
+
+def test_softmax_sampling(oracle):
+    # r = 53-bit uniform from (rnd[0], rnd[1]); index = first running sum > r, else the last
+    q = [0.0, 1.0]
+    p0 = 1 / (1 + np.e)
+    lo = int(p0 * 2 ** 32) - 1
+    assert oracle.policy_sample(abi.SOFTMAX, 1.0, q, [lo, 0, 0, 0])[0] == 0
+    assert oracle.policy_sample(abi.SOFTMAX, 1.0, q, [lo + 2, 0, 0, 0])[0] == 1
+    assert oracle.policy_sample(abi.SOFTMAX, 1.0, q, [0xFFFFFFFF, 0xFFFFFFFF, 0, 0])[0] == 1
+    rng = np.random.default_rng(0)
+    counts = np.zeros(2)
+    for _ in range(20000):
+        counts[oracle.policy_sample(abi.SOFTMAX, 1.0, q, rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32))[0]] += 1
+    assert np.abs(counts / 20000 - [p0, 1 - p0]).max() < 1e-2            # test_2d
