@@ -47,6 +47,37 @@ for dtype, tol, horizon in ((abi.F64, 1e-11, None), (abi.F32, 1e-4, 12)):
             single.close()
         eng.close()
         dist.barrier()
+# BASELINE config 5: SARSA(lambda) with per-env eligibility traces (resident in shared memory), shared W exchanged in-kernel.
+# f64 is the correctness check (agreement with a single-GPU engine to 1e-10).  In f32 the different summation order of dW
+# flips near-tied eps-greedy decisions from the second step on and the trajectories diverge chaotically (measured 5e-2 after
+# 12 steps on 2 GPUs): there the check is bit-identical replicas and a bounded difference.
+for dtype, tol, steps in ((abi.F64, 1e-10, 120), (abi.F32, 0.2, 12)):
+    n_global = 32768 * world if dtype == abi.F32 else 2048 * world + 37
+    kw = dict(dtype=dtype, algo=abi.SARSA_LAMBDA, policy=abi.EPSILON_GREEDY, epsilon=0.2, alpha=0.01, gamma=0.99, init_mode=abi.INIT_UNIFORM,
+              init_lo=[-0.6, 0.0], init_hi=[-0.4, 0.0], max_episode_steps=150, seed=4, update_scale=abi.SCALE_MEAN)
+    lo, hi = shard_range(n_global, rank, world)
+    eng = Engine(abi.default_config(n_envs=hi - lo, env_offset=lo, n_envs_global=n_global, device=local, **kw))
+    handles = [None] * world
+    dist.all_gather_object(handles, eng.peer_export())
+    eng.peer_attach(handles, rank, world)
+    dist.barrier()
+    eng.step(steps); eng.sync()
+    W = torch.from_numpy(eng.weights()).cuda()
+    allW = [torch.empty_like(W) for _ in range(world)]
+    dist.all_gather(allW, W)
+    replicas_identical = all(bool((w == allW[0]).all()) for w in allW)
+    if rank == 0:
+        single = Engine(abi.default_config(n_envs=n_global, device=local, **kw))
+        single.step(steps); single.sync()
+        werr = np.abs(eng.weights() - single.weights()).max() / max(np.abs(single.weights()).max(), 1e-30)
+        good = replicas_identical and werr < tol
+        ok &= good
+        print(f"cfg5 sarsa(lambda) dtype={'f64' if dtype == abi.F64 else 'f32'} N={n_global} world={world}: replicas_identical={replicas_identical} "
+              f"|W - W_single|/|W|max={werr:.3e} launches={eng.stats()['kernel_launches']} -> {'OK' if good else 'FAIL'}", flush=True)
+        single.close()
+    eng.close()
+    dist.barrier()
+
 # BASELINE config 4: Acrobot / ExpectedSARSA / Fourier(7) on the tensor-core path, envs sharded over the ranks, dW (4096 x 3)
 # summed with ncclAllReduce between the dW pass and the weight update
 from rsrl_b200.engine import comm_unique_id
