@@ -401,7 +401,8 @@ __device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* co
     return h;
 }
 
-template <class Dom>
+// TMAX: compile-time bound of the tiling loops (>= tp.n_tilings); 8 halves the unrolled hash / dedup code of 8-tiling configs
+template <class Dom, int TMAX = kMaxTilings>
 __device__ __forceinline__ void tile_prepare(const double* st, const TileParams& tp, TileTab& tab) {
     int32_t q[Dom::D];
 #pragma unroll
@@ -411,7 +412,7 @@ __device__ __forceinline__ void tile_prepare(const double* st, const TileParams&
     }
     tab.n = 0;
 #pragma unroll
-    for (int t = 0; t < kMaxTilings; ++t) {
+    for (int t = 0; t < TMAX; ++t) {
         if (t < tp.n_tilings) {
             int32_t coord[Dom::D];
 #pragma unroll
@@ -419,10 +420,10 @@ __device__ __forceinline__ void tile_prepare(const double* st, const TileParams&
             const int32_t row = (int32_t)(tile_hash((uint32_t)t, coord, Dom::D) & (uint32_t)tp.memory_mask);
             bool dup = false;
 #pragma unroll
-            for (int j = 0; j < kMaxTilings; ++j) dup |= (j < tab.n) && tab.idx[j] == row;
+            for (int j = 0; j < TMAX; ++j) dup |= (j < tab.n) && tab.idx[j] == row;
             if (!dup) {
 #pragma unroll
-                for (int j = 0; j < kMaxTilings; ++j) if (j == tab.n) tab.idx[j] = row;  // register-friendly insert
+                for (int j = 0; j < TMAX; ++j) if (j == tab.n) tab.idx[j] = row;  // register-friendly insert
                 tab.n += 1;
             }
         }

@@ -139,7 +139,7 @@ __device__ __forceinline__ void grid_barrier_local(unsigned long long* counter, 
     __syncthreads();
 }
 
-template <typename R, int DOM, int AW, bool EXT, int MAXT = 512>
+template <typename R, int DOM, int AW, bool EXT, int MAXT = 512, int TMAX = kMaxTilings>
 __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, const int k_steps, const TileArgs ta) {
     using Dom = Domain<DOM>;
     constexpr int D = Dom::D;
@@ -162,14 +162,14 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
 #pragma unroll
         for (int c = 0; c < AW; ++c) q[c] = (R)0;
 #pragma unroll
-        for (int j = 0; j < kMaxTilings; ++j) {
+        for (int j = 0; j < TMAX; ++j) {
             if (j < tab.n) {
 #pragma unroll
                 for (int c = 0; c < AW; ++c) q[c] += Wsm[tab.idx[j] * AW + c];  // activation 1.0
             }
         }
     };
-    auto prep = [&](const double* st, TileTab& tb) { tile_prepare<Dom>(st, ta.tp, tb); };
+    auto prep = [&](const double* st, TileTab& tb) { tile_prepare<Dom, TMAX>(st, ta.tp, tb); };
     const double inv_fx = 1.0 / ta.fx_scale;
     unsigned long long* P = ta.G;                          // [G][MA]
     unsigned long long* T = ta.G + (size_t)G * MA;         // [MA]
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
             // dW[row, a_t] += coef for every active row (activation 1.0).  When the whole warp hits the same entry (envs
             // start in the same tiles) the warp adds once.
 #pragma unroll
-            for (int j = 0; j < kMaxTilings; ++j) {
+            for (int j = 0; j < TMAX; ++j) {
                 if (j >= ta.tp.n_tilings) break;  // uniform
                 const int key = (active && j < tab_s.n) ? tab_s.idx[j] * AW + col : -1;
                 int same;

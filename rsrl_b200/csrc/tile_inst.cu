@@ -11,10 +11,13 @@ typedef RSRL_REAL R;
 template <int DOM, int AW, bool EXT>
 static cudaError_t tile_one(const StepArgs& a, int k_steps, const TileArgs& ta, int grid, int block, size_t smem, cudaStream_t st) {
     // dense kernel: 512 threads (128 registers each) or up to 1024 (64 registers: spills, but twice the warps to hide the f64 latencies)
+    // TMAX = 8 instantiation: half the unrolled tiling loops for the common <= 8 tilings
     auto kern = !ta.dense ? tile_persistent_kernel<R, DOM, AW, EXT>
-                          : (block > 768 ? tile_dense_kernel<R, DOM, AW, EXT, 1024> : block > 512 ? tile_dense_kernel<R, DOM, AW, EXT, 768> : tile_dense_kernel<R, DOM, AW, EXT, 512>);
-    static size_t configured_v[4] = {0, 0, 0, 0};
-    size_t& configured = configured_v[!ta.dense ? 0 : block > 768 ? 3 : block > 512 ? 2 : 1];
+              : ta.tp.n_tilings <= 8
+                    ? (block > 768 ? tile_dense_kernel<R, DOM, AW, EXT, 1024, 8> : block > 512 ? tile_dense_kernel<R, DOM, AW, EXT, 768, 8> : tile_dense_kernel<R, DOM, AW, EXT, 512, 8>)
+                    : (block > 768 ? tile_dense_kernel<R, DOM, AW, EXT, 1024> : block > 512 ? tile_dense_kernel<R, DOM, AW, EXT, 768> : tile_dense_kernel<R, DOM, AW, EXT, 512>);
+    static size_t configured_v[7] = {0, 0, 0, 0, 0, 0, 0};
+    size_t& configured = configured_v[!ta.dense ? 0 : (block > 768 ? 3 : block > 512 ? 2 : 1) + (ta.tp.n_tilings <= 8 ? 3 : 0)];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
