@@ -302,7 +302,7 @@ def main():
                      domain=abi.CART_POLE, basis=abi.TILE_CODING, algo=abi.SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99,
                      lr=0.1 / 8, init_lo=[-0.05] * 4, init_hi=[0.05] * 4, max_episode_steps=500)
         c3["roofline"] = {"bound": "hbm", "achieved": 80 * c3["value"] / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 80 * c3["value"] / 1e9 / peak_gbs,
-                          "note": "algorithmic 80 B/env-step (SURVEY 8d); binding roof: f64 RK4 latency at 16 warps/SM (profiles/r01_final.md)"}
+                          "note": "algorithmic 80 B/env-step (SURVEY 8d); binding roof: instruction issue of the f64 RK4 + tile hashing, 4.7 k instructions per env-step (profiles/r01_final.md)"}
         c4 = cfg_run("cfg4 shard: Acrobot ExpectedSARSA Fourier(7)+bias (F=4096) eps-greedy, 131072 envs, SHARED, tcgen05 3xTF32 path", 40, 131072,
                      domain=abi.ACROBOT, basis_order=7, algo=abi.EXPECTED_SARSA, policy=abi.EPSILON_GREEDY, epsilon=0.1, gamma=0.99, lr=1e-4,
                      alpha=1.0, init_lo=[-0.1] * 4, init_hi=[0.1] * 4, max_episode_steps=500)
