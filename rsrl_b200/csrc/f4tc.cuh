@@ -13,8 +13,8 @@
 //                                               dW[m,n] = sum_env ur_m (vr_n' d_a) + ui_m (-vi_n' d_a)
 //                   -> one [128 x K] x [K x 32A] GEMM with K = 2 x envs, accumulated in TMEM over all envs of a CTA.
 //
-// Both run as kind::tf32 tcgen05.mma with the operands split x = hi + lo (hi, lo both TF32-representable) and
-// three passes hi*hi + lo*hi + hi*lo ("3xTF32"): per-product error ~2^-22, fp32 accumulation — fp32-grade results
+// Both run as kind::tf32 tcgen05.mma with the operands split x = hi + lo (hi = x rounded to TF32, lo = x - hi) and
+// three products hi*hi + lo*hi + hi*lo ("3xTF32"): per-product error ~2^-21, fp32 accumulation — fp32-grade results
 // (tools/microbench/umma_tf32.cu measures 1.2e-5 max error on K = 64 sums of O(1) terms vs 7.6e-3 for plain TF32).
 // Operand tiles are GENERATED on chip (never read from HBM) by the CTA's threads straight into the canonical
 // no-swizzle K-major UMMA layout; the accumulators live in TMEM and are read back with tcgen05.ld.
