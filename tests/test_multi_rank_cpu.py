@@ -39,13 +39,15 @@ def _worker(rank, world, port, n_global, steps, kw, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["shared", "per_env"])
+@pytest.mark.parametrize("mode", ["shared", "per_env", "shared_pal_softmax"])
 def test_two_rank_sharding_matches_single_rank(oracle, tmp_path, mode):
     import torch.multiprocessing as mp
     from rsrl_b200 import abi
     kw = dict(dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[-0.4, 0.0], max_episode_steps=40,
               seed=5, policy=abi.EPSILON_GREEDY, epsilon=0.2, update_scale=abi.SCALE_MEAN,
-              weight_mode=abi.SHARED if mode == "shared" else abi.PER_ENV)
+              weight_mode=abi.PER_ENV if mode == "per_env" else abi.SHARED)
+    if mode == "shared_pal_softmax":   # PAL agent (control/td/pal.rs) behind a Softmax policy (tau = 0.5 in the epsilon field)
+        kw.update(algo=abi.PAL, policy=abi.SOFTMAX, epsilon=0.5, alpha=0.5, lr=0.01)
     n_global, steps, world = 37, 60, 2   # ragged split: 19 + 18 envs
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n_global, steps, kw, str(tmp_path)), nprocs=world, join=True)
@@ -59,7 +61,7 @@ def test_two_rank_sharding_matches_single_rank(oracle, tmp_path, mode):
     hashes = np.concatenate([p["hash"] for p in parts])
     assert (actions == single.actions()).all() and (hashes == single.env_stats()[2]).all()
     assert np.abs(states - single.states()).max() < 1e-12
-    if mode == "shared":
+    if mode != "per_env":
         # both ranks hold the same replicated W; it equals the single-rank W up to summation order
         assert (parts[0]["weights"] == parts[1]["weights"]).all()
         assert np.abs(parts[0]["weights"] - single.weights()).max() < 1e-12
