@@ -770,21 +770,22 @@ __global__ void __launch_bounds__(544, 1) f4tc_dw_kernel(int64_t n, const float*
     if (q == 0) tc::tmem_free<TMEM_COLS>(tmem);
 }
 
-// Fixed-order sum of the per-CTA partials: block = 8 warps x 32 consecutive weights; warp w adds partials w, w+8, ...
-// in ascending order, the 8 warp sums are added in warp order.  W += sum (single GPU) or dW_out = sum (exchange).
-__global__ void __launch_bounds__(256) f4tc_reduce_kernel(const float* __restrict__ partials, int n_partials, int fa, float* __restrict__ W,
-                                                          float* __restrict__ dW_out) {
-    __shared__ float part[8][32];
+// Fixed-order sum of the per-CTA partials: block = 32 warps x 32 consecutive weights; warp w adds partials w, w+32, ...
+// in ascending order (<= 5 loads per thread for 148 partials: latency, not bandwidth, bounds this kernel), the 32 warp
+// sums are added in warp order.  W += sum (single GPU) or dW_out = sum (exchange).
+__global__ void __launch_bounds__(1024) f4tc_reduce_kernel(const float* __restrict__ partials, int n_partials, int fa, float* __restrict__ W,
+                                                           float* __restrict__ dW_out) {
+    __shared__ float part[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, j = blockIdx.x * 32 + lane;
     float acc = 0.0f;
     if (j < fa)
-        for (int p = w; p < n_partials; p += 8) acc += partials[(size_t)p * fa + j];
+        for (int p = w; p < n_partials; p += 32) acc += partials[(size_t)p * fa + j];
     part[w][lane] = acc;
     __syncthreads();
     if (w == 0 && j < fa) {
         float g = part[0][lane];
 #pragma unroll
-        for (int x = 1; x < 8; ++x) g += part[x][lane];
+        for (int x = 1; x < 32; ++x) g += part[x][lane];
         if (dW_out) dW_out[j] = g;
         else W[j] += g;
     }

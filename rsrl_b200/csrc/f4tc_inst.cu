@@ -58,7 +58,7 @@ cudaError_t launch_f4tc_dw(int domain, int64_t n, const float* tabs, const void*
 }
 
 cudaError_t launch_f4tc_reduce(const void* partials, int n_partials, int fa, void* W, void* dW_out, cudaStream_t st) {
-    f4tc_reduce_kernel<<<(fa + 31) / 32, 256, 0, st>>>(static_cast<const float*>(partials), n_partials, fa, static_cast<float*>(W),
+    f4tc_reduce_kernel<<<(fa + 31) / 32, 1024, 0, st>>>(static_cast<const float*>(partials), n_partials, fa, static_cast<float*>(W),
                                                       static_cast<float*>(dW_out));
     return cudaGetLastError();
 }
