@@ -176,6 +176,16 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
                        const double* rewards, const double* to_states, const uint8_t* terminal,
                        uint64_t draw, double* td_out);
 
+/* ---- introspection for the parity tests ---- */
+/* Launch shape of the fused loop: out = {persistent kernel in use, its mode, CTAs, cluster size, clusters, threads per CTA,
+ * LL lanes per row, reducer lanes per row group, slots per reducer lane, PER_ENV weights in shared memory, world, rank,
+ * peers attached, dynamic shared memory bytes, TileCoding engine, large-basis engine (1 + tensor-core bits)}.
+ * The order of the fp32 dW sums is a function of these numbers; oracle/oracle32.cpp replays it on the host. */
+int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[16]);
+/* The elementary functions of the device arithmetic (csrc/device.cuh "rsrl math") evaluated on the GPU:
+ * fn 0 cos (f64), 1 sin (f64), 2 sin(pi x) (fp32), 3 cos(pi x) (fp32), 4 exp (fp32). */
+int rsrl_math_probe(int32_t fn, int64_t n, const double* x, double* out);
+
 /* ---- multi-GPU (one process per GPU; SHARED mode exchanges dW every step) ---- */
 int rsrl_comm_unique_id(uint8_t out[128]);                      /* ncclGetUniqueId on rank 0 */
 int rsrl_engine_comm_init(rsrl_engine_t* e, const uint8_t id[128], int rank, int world);

@@ -340,7 +340,48 @@ class Engine:
         return td
 
 
-def baseline_run(cfg, threads, envs_per_thread, steps):
+NATIVE_PATH = os.path.join(HERE, "_build", "librsrl_oracle_native.so")
+_native = None
+
+
+def native_lib():
+    """rsrl_oracle.c rebuilt -O3 -march=native ON THIS MACHINE for the CPU-baseline timing (BASELINE.md section 3);
+    never shipped (a -march=native binary may not run elsewhere).  Falls back to the portable build if gcc is missing."""
+    global _native
+    if _native is None:
+        try:
+            subprocess.check_call(["make", "-C", HERE, "-s", "-B", "native"])
+            L = C.CDLL(NATIVE_PATH)
+            kind = "-O3 -march=native"
+        except (OSError, subprocess.CalledProcessError):
+            L, kind = lib(), "-O2 (portable build: native rebuild failed)"
+        for name in ("orc_baseline_run", "orc_baseline_run_fused"):
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = C.c_double, [_cfgp, C.c_int, C.c_int64, C.c_int64, _P(C.c_int64)]
+        L.orc_baseline_run_single.restype = C.c_double
+        L.orc_baseline_run_single.argtypes = [_cfgp, C.c_int64, _ip, C.c_int, _P(C.c_int64)]
+        _native = (L, kind)
+    return _native
+
+
+def baseline_run(cfg, threads, envs_per_thread, steps, fused=False):
+    """(seconds of stepping, env-steps done): `threads` x envs_per_thread independent single-env agents, reference-shaped
+    (4 projections + heap allocations per step) or fused=True (1 projection, no allocation)."""
+    L, _ = native_lib()
     done = C.c_int64()
-    secs = lib().orc_baseline_run(C.byref(cfg), threads, envs_per_thread, steps, C.byref(done))
+    fn = L.orc_baseline_run_fused if fused else L.orc_baseline_run
+    secs = fn(C.byref(cfg), threads, envs_per_thread, steps, C.byref(done))
     return secs, done.value
+
+
+def baseline_run_single(cfg, steps, n_ep_lens=40):
+    """BASELINE configs[0]: one env on one core; returns (seconds, env-steps, first episode lengths)."""
+    L, _ = native_lib()
+    done = C.c_int64()
+    lens = np.zeros(n_ep_lens, dtype=np.int32)
+    secs = L.orc_baseline_run_single(C.byref(cfg), steps, _i(lens), n_ep_lens, C.byref(done))
+    return secs, done.value, [int(x) for x in lens if x >= 0]
+
+
+def baseline_build_flags():
+    return native_lib()[1]

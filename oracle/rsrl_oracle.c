@@ -738,37 +738,129 @@ void orc_engine_set_epsilon(orc_engine_t* e, double eps) { e->cfg.epsilon = eps;
 double orc_engine_min_gap(orc_engine_t* e) { return e->min_gap; }
 
 /* ------------------------------------------------------------------------- */
-/* CPU baseline: `threads` workers, each a batch of independent reference agents */
+/* CPU baseline: `threads` workers, each a batch of independent reference-shaped
+ * single-env agents.  Engines are created and the threads are started BEFORE the clock starts (a barrier
+ * releases them together); only stepping is timed. */
 /* ------------------------------------------------------------------------- */
-typedef struct { rsrl_config_t cfg; int64_t steps; int64_t done; } worker_t;
+typedef struct {
+    rsrl_config_t cfg; int64_t steps; int64_t done; int fused;
+    pthread_barrier_t* start; pthread_barrier_t* stop;
+    int32_t* ep_lens; int n_ep_lens; /* optional: first episode lengths of env 0 (single-env runs) */
+} worker_t;
+
+/* The best simple scalar CPU implementation of the same step (not the reference's cost structure): one projection
+ * per env-step (phi(s') becomes phi(s)), Q(s_{t+1}) re-evaluated after the update like the reference does, no heap
+ * allocation.  Q-learning / SARSA / ExpectedSARSA with PER_ENV weights (N independent agents). */
+static void fused_steps(orc_engine_t* e, int64_t steps) {
+    const rsrl_config_t* c = &e->cfg;
+    const int A = e->AW;
+    const int64_t F = e->F;
+    double* phi = (double*)malloc((size_t)(e->N * F) * sizeof(double));
+    double* nphi = (double*)malloc((size_t)F * sizeof(double));
+    for (int64_t i = 0; i < e->N; ++i) orc_basis_project(c, e->s + i * e->D, phi + i * F);
+    for (int64_t t = 0; t < steps; ++t) {
+        for (int64_t i = 0; i < e->N; ++i) {
+            const int64_t g = c->env_offset + i;
+            double* W = e->W + i * F * A;
+            double* s = e->s + i * e->D;
+            double* ph = phi + i * F;
+            double q[16], nq[16], r, target = 0.0;
+            uint32_t rnd[4];
+            int nf = 0, term;
+            for (int a = 0; a < A; ++a) { double acc = 0.0; for (int64_t k = 0; k < F; ++k) acc = acc + ph[k] * W[k * A + a]; q[a] = acc; }
+            orc_draw(c->seed, (uint64_t)g, (uint64_t)e->t, STREAM_BEHAVIOUR, rnd);
+            const int act = orc_policy_sample(c->policy, c->epsilon, q, A, rnd, &nf);
+            orc_domain_step(c->domain, s, act, &r, &term);
+            if (!term) {
+                orc_basis_project(c, s, nphi);
+                for (int a = 0; a < A; ++a) { double acc = 0.0; for (int64_t k = 0; k < F; ++k) acc = acc + nphi[k] * W[k * A + a]; nq[a] = acc; }
+                if (c->algo == RSRL_QLEARNING) orc_find_max(nq, A, &target);
+                else if (c->algo == RSRL_SARSA) { orc_draw(c->seed, (uint64_t)g, (uint64_t)e->t, STREAM_TARGET, rnd); target = nq[orc_policy_sample(c->policy, c->epsilon, nq, A, rnd, &nf)]; }
+                else { double p[16]; orc_policy_probs(c->policy, c->epsilon, nq, A, p); for (int a = 0; a < A; ++a) target = target + nq[a] * p[a]; }
+            }
+            const double residual = term ? r - q[act] : r + c->gamma * target - q[act];
+            const double lr_err = c->lr * (c->algo == RSRL_EXPECTED_SARSA ? c->alpha * residual : residual);
+            for (int64_t k = 0; k < F; ++k) W[k * A + act] = W[k * A + act] + lr_err * ph[k];
+            e->a[i] = act;
+            e->ep[i] += 1;
+            e->st.total_steps += 1;
+            if (term || (c->max_episode_steps > 0 && e->ep[i] >= c->max_episode_steps)) {
+                e->st.total_episodes += 1;
+                e->n_ep[i] += 1; e->last_len[i] = e->ep[i];
+                e->len_hash[i] = e->len_hash[i] * 1000003ull + (uint64_t)e->ep[i];
+                e->ep[i] = 0;
+                fresh_state(e, g, e->t + 1, s);
+                orc_basis_project(c, s, ph);
+            } else {
+                memcpy(ph, nphi, (size_t)F * sizeof(double));
+            }
+        }
+        e->t += 1;
+    }
+    free(phi); free(nphi);
+}
 
 static void* worker_main(void* p) {
     worker_t* w = (worker_t*)p;
     orc_engine_t* e = orc_engine_create(&w->cfg);
-    orc_engine_step(e, w->steps);
+    pthread_barrier_wait(w->start);
+    if (w->fused) {
+        fused_steps(e, w->steps);
+    } else if (w->ep_lens) { /* single env: record the first episode lengths while stepping */
+        int got = 0;
+        for (int64_t t = 0; t < w->steps; ++t) {
+            orc_engine_step(e, 1);
+            if (got < w->n_ep_lens && e->n_ep[0] > got) w->ep_lens[got++] = e->last_len[0];
+        }
+        for (; got < w->n_ep_lens; ++got) w->ep_lens[got] = -1;
+    } else {
+        orc_engine_step(e, w->steps);
+    }
+    pthread_barrier_wait(w->stop);
     w->done = e->st.total_steps;
     orc_engine_destroy(e);
     return NULL;
 }
 
-double orc_baseline_run(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int64_t* out_steps) {
+static double run_workers(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int fused,
+                          int32_t* ep_lens, int n_ep_lens, int64_t* out_steps) {
     pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
     worker_t* w = (worker_t*)calloc((size_t)threads, sizeof(worker_t));
+    pthread_barrier_t start, stop;
     struct timespec t0, t1;
     int64_t total = 0;
+    pthread_barrier_init(&start, NULL, (unsigned)threads + 1);
+    pthread_barrier_init(&stop, NULL, (unsigned)threads + 1);
     for (int i = 0; i < threads; ++i) {
         w[i].cfg = *cfg;
         w[i].cfg.weight_mode = RSRL_PER_ENV; /* one agent per env: the only shape the Rc-based reference admits */
         w[i].cfg.n_envs = envs_per_thread;
         w[i].cfg.env_offset = cfg->env_offset + (int64_t)i * envs_per_thread;
-        w[i].steps = steps;
+        w[i].steps = steps; w[i].fused = fused; w[i].start = &start; w[i].stop = &stop;
+        w[i].ep_lens = i == 0 ? ep_lens : NULL; w[i].n_ep_lens = n_ep_lens;
+        pthread_create(&th[i], NULL, worker_main, &w[i]);
     }
+    pthread_barrier_wait(&start); /* every engine exists */
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, worker_main, &w[i]);
-    for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+    pthread_barrier_wait(&stop);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
     for (int i = 0; i < threads; ++i) total += w[i].done;
     if (out_steps) *out_steps = total;
+    pthread_barrier_destroy(&start); pthread_barrier_destroy(&stop);
     free(th); free(w);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double orc_baseline_run(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int64_t* out_steps) {
+    return run_workers(cfg, threads, envs_per_thread, steps, 0, NULL, 0, out_steps);
+}
+
+double orc_baseline_run_fused(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int64_t* out_steps) {
+    return run_workers(cfg, threads, envs_per_thread, steps, 1, NULL, 0, out_steps);
+}
+
+/* BASELINE configs[0] = examples/q_learning.rs on one core: `steps` env-steps of ONE env; the first n_ep_lens episode lengths. */
+double orc_baseline_run_single(const rsrl_config_t* cfg, int64_t steps, int32_t* ep_lens, int n_ep_lens, int64_t* out_steps) {
+    return run_workers(cfg, 1, 1, steps, 0, ep_lens, n_ep_lens, out_steps);
 }

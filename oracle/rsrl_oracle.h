@@ -90,8 +90,13 @@ void orc_engine_handle(orc_engine_t* e, int64_t n, const double* from, const int
                        const double* to, const uint8_t* terminal, uint64_t draw, double* td_out);
 
 /* ---- CPU baseline: `threads` independent reference-shaped single-env agents, `steps` env-steps each;
- * returns wall seconds; *out_steps = env-steps executed */
+ * returns wall seconds of the stepping alone (engines are created and threads started before the clock); *out_steps = env-steps executed */
 double orc_baseline_run(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int64_t* out_steps);
+/* the same agents as a fused scalar loop: one projection per env-step, no heap allocation (the best simple CPU implementation;
+ * Q-learning / SARSA / ExpectedSARSA).  Reported next to the reference-shaped number, BASELINE.md section 3. */
+double orc_baseline_run_fused(const rsrl_config_t* cfg, int threads, int64_t envs_per_thread, int64_t steps, int64_t* out_steps);
+/* one env on one core (examples/q_learning.rs itself); ep_lens receives the first n_ep_lens episode lengths (-1: not reached) */
+double orc_baseline_run_single(const rsrl_config_t* cfg, int64_t steps, int32_t* ep_lens, int n_ep_lens, int64_t* out_steps);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,8 @@ SYMBOLS = {
     "rsrl_engine_sample": (C.c_int, [_eng, C.c_int64, _dp, C.c_uint64, _ip]),
     "rsrl_engine_mode": (C.c_int, [_eng, C.c_int64, _dp, _ip]),
     "rsrl_engine_handle": (C.c_int, [_eng, C.c_int64, _dp, _ip, _dp, _dp, _u8p, C.c_uint64, _dp]),
+    "rsrl_engine_get_launch_shape": (C.c_int, [_eng, _ip]),
+    "rsrl_math_probe": (C.c_int, [C.c_int32, C.c_int64, _dp, _dp]),
     "rsrl_comm_unique_id": (C.c_int, [_u8p]),
     "rsrl_engine_comm_init": (C.c_int, [_eng, _u8p, C.c_int, C.c_int]),
     "rsrl_engine_peer_export": (C.c_int, [_eng, _u8p]),

@@ -11,7 +11,9 @@ LIB = os.path.join(CSRC, "librsrl_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
-HEADERS = ["device.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
+# --fmad=false for the units whose arithmetic oracle/oracle32.cpp reproduces bit for bit: every FMA there is explicit (hostdev.h)
+NOFMAD = ["--fmad=false"]
+HEADERS = ["hostdev.h", "device.cuh", "core.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
 
 
 # headers only some translation units include (kept out of HEADERS so that editing them does not rebuild everything)
@@ -22,13 +24,13 @@ def _units():
     # RSRL_BUILD_DOMAINS=0 (development only) leaves the CartPole / Acrobot instantiations out for fast iteration;
     # the default builds everything.
     doms = {int(d) for d in os.environ.get("RSRL_BUILD_DOMAINS", "0,1,2").split(",")}
-    units = [("abi.o", "abi.cu", []), ("f4tc.o", "f4tc_inst.cu", [])]
+    units = [("abi.o", "abi.cu", NOFMAD), ("f4tc.o", "f4tc_inst.cu", [])]
     for rname, rtype in (("f32", "float"), ("f64", "double")):
         units.append((f"tile_{rname}.o", "tile_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
         units.append((f"f4_{rname}.o", "f4_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
         for dom in (0, 1, 2):
             suffix = f"{rname}_d{dom}"
-            defs = [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"]
+            defs = [f"-DRSRL_REAL={rtype}", f"-DRSRL_DOM={dom}", f"-DRSRL_SUFFIX={suffix}"] + NOFMAD
             if dom not in doms:
                 defs.append("-DRSRL_EMPTY")
                 units.append((f"inst_{suffix}_empty.o", "inst.cu", defs))

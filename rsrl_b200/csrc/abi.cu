@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -68,7 +69,15 @@ static int validate(const rsrl_config_t* c) {
     if (c->policy < 0 || c->policy > RSRL_SOFTMAX) return fail(RSRL_EINVAL, "unknown policy");
     if (c->dtype != RSRL_F32 && c->dtype != RSRL_F64) return fail(RSRL_EINVAL, "unknown dtype");
     if (c->weight_mode != RSRL_SHARED && c->weight_mode != RSRL_PER_ENV) return fail(RSRL_EINVAL, "unknown weight_mode");
+    if (c->trace_rule < RSRL_TRACE_ACCUMULATE || c->trace_rule > RSRL_TRACE_DUTCH) return fail(RSRL_EINVAL, "unknown trace_rule");
+    if (c->update_scale != RSRL_SCALE_SUM && c->update_scale != RSRL_SCALE_MEAN) return fail(RSRL_EINVAL, "unknown update_scale");
+    if (c->init_mode != RSRL_INIT_DEFAULT && c->init_mode != RSRL_INIT_UNIFORM) return fail(RSRL_EINVAL, "unknown init_mode");
+    if (!std::isfinite(c->lr) || !std::isfinite(c->alpha) || !std::isfinite(c->gamma) || !std::isfinite(c->lambda) || !std::isfinite(c->epsilon))
+        return fail(RSRL_EINVAL, "lr, alpha, gamma, lambda and epsilon must be finite");
     if (c->n_envs <= 0) return fail(RSRL_EINVAL, "n_envs must be > 0");
+    if (c->n_envs_global != 0 && c->n_envs_global < c->env_offset + c->n_envs)
+        return fail(RSRL_EINVAL, "n_envs_global must cover env_offset + n_envs (or be 0)");
+    if (c->max_episode_steps < 0) return fail(RSRL_EINVAL, "max_episode_steps must be >= 0");
     if (c->env_offset < 0 || c->env_offset + c->n_envs > 0xFFFFFFFFll) return fail(RSRL_EINVAL, "global env ids must fit 32 bits");
     if (c->policy == RSRL_SOFTMAX) {
         if (!(c->epsilon <= -1e-7 || c->epsilon >= 1e-7)) return fail(RSRL_EINVAL, "Softmax: the temperature tau (epsilon field) must be non-zero (softmax.rs:61-64)");
@@ -123,10 +132,10 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     return table[k.dtype][k.domain](k, e, st);
 }
 
-static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st, int* max_clusters = nullptr) {
     static const persist_launch_fn table[2][3] = {{launch_persist_f32_d0, launch_persist_f32_d1, launch_persist_f32_d2},
                                                   {launch_persist_f64_d0, launch_persist_f64_d1, launch_persist_f64_d2}};
-    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, pe, grid, block, smem, st);
+    return table[k.dtype][k.domain](k, mode, a, k_steps, sy, pe, grid, block, smem, st, max_clusters);
 }
 
 static int unsupported(const rsrl_config_t* c) {
@@ -193,8 +202,9 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, nullptr, 0, 0, 1, 1, 4, 0, 0};
-    size_t sync1_bytes = 0, sync2_bytes = 0, stage3_bytes = 0;
+    SyncArgs sync = {nullptr, 1, 1, 1, 1, 4, 0, 0, 0u};
+    size_t stage_bytes = 0;
+    uint32_t xepoch = 0;  // exchange epoch: counts batched steps over the engine's life, NOT reset by rsrl_engine_reset
     int pcap = 0;  // padded slot count of the CTA reduce buffers
     uint64_t t = 0;
     int64_t launches = 0;
@@ -215,7 +225,7 @@ struct rsrl_engine {
     int rank = 0, world = 1;
     // in-kernel exchange over peer memory (persistent.cuh hop 3)
     PeerArgs peer;
-    uint2* inbox = nullptr;      // this rank's mailbox [2][kMaxRanks][FA * WPV]
+    uint2* inbox = nullptr;      // this rank's mailbox [2][kMaxRanks][n_clusters][FA * WPV]
     size_t inbox_bytes = 0;
     void* peer_mapped[kMaxRanks] = {nullptr};
     bool peers_attached = false;
@@ -248,41 +258,19 @@ static void choose_launch(rsrl_engine* e) {
     e->grid = (int)((e->N + e->block - 1) / e->block);
 }
 
-// Shape of the persistent kernel: one CTA per SM (SHARED: co-resident, spins on LL flags), one env per
-// thread when the shard fits (state stays in registers), F-wide reducer lanes need block >= F.
-static void choose_persistent(rsrl_engine* e) {
-    e->persistent = false;
-    e->pmode = e->cfg.weight_mode;
-    if (e->has_trace && e->cfg.weight_mode == RSRL_PER_ENV) return;  // per-env W + traces: per-step kernels
-    int dev = e->cfg.device, sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) return;
+// Shape of the persistent kernel: one CTA per SM, grouped in thread-block clusters (SHARED: all co-resident, they wait for
+// each other every step), one env per thread when the shard fits (state stays in registers), block >= reduce rows.
+static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
     auto round32 = [](int64_t x) { return (int)((x + 31) / 32 * 32); };
-    if (e->cfg.weight_mode == RSRL_PER_ENV) {
-        e->pblock = 128;
-        e->pgrid = (int)((e->N + e->pblock - 1) / e->pblock);
-        // every env's own W in shared memory (F*A x 128 columns) when at least two CTAs still fit on an SM
-        const size_t wbytes = (size_t)e->FA * e->pblock * e->rsz;
-        e->sync.pe_smem = wbytes <= 110 * 1024 ? 1 : 0;
-        e->psmem = e->sync.pe_smem ? wbytes : 0;
-        e->persistent = true;
-        return;
-    }
-    int grid = (int)((e->N + 127) / 128);
-    if (grid > sms) grid = sms;
-    if (grid > kMaxFan * kMaxFan) grid = kMaxFan * kMaxFan;
     const int64_t per_cta = (e->N + grid - 1) / grid;
     const int64_t rows = e->has_trace ? e->FA : e->F;  // traces: z (F*A rows) lives in shared memory for the whole launch
-    if (e->has_trace) {
-        if (per_cta > 512) return;  // needs one env per thread
-        e->pmode = kModeSharedTrace;
-    }
+    if (e->has_trace && per_cta > 512) return false;   // needs one env per thread
     int block = round32(per_cta);
     if (block < round32(rows)) block = round32(rows);
     if (block < 64) block = 64;
     if (block > 512) block = 512;
-    if (block < rows) return;
-    // persistent.cuh shapes: lpr adjacent lanes own one row in the LL exchange; lpg adjacent lanes own a
+    if (block < rows) return false;
+    // persistent.cuh shapes: lpr adjacent lanes own one row in the exchanges between cluster leaders; lpg adjacent lanes own a
     // group of 4 rows in the CTA reduce, each lane summing one slot segment of seg_len slots.
     const int vn = (int)(16 / e->rsz);
     int lpr = 8;
@@ -294,17 +282,61 @@ static void choose_persistent(rsrl_engine* e) {
     if ((seg_len / vn) % 2 == 0) seg_len += vn;  // odd number of 16-byte groups: conflict-free segment reads
     const int cap = lpg * seg_len;
     const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;
-    const size_t elems = (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap + (size_t)nrg * 4 * ndc;
-    const size_t bytes = elems * e->rsz;
+    const size_t nvp = (size_t)persist_nvp((int)e->FA, (int)e->rsz);
+    const size_t elems = (size_t)(2 + cs) * nvp + (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap;
+    const size_t bytes = 16 + elems * e->rsz;
+    if (bytes > 220 * 1024) return false;
     e->pcap = cap;
     e->sync.lpr = lpr; e->sync.lpg = lpg; e->sync.seg_len = seg_len;
-    e->sync.debug_skip = getenv("RSRL_B200_DEBUG_SKIP") ? atoi(getenv("RSRL_B200_DEBUG_SKIP")) : 0;
-    if (bytes > 220 * 1024) return;
+    e->sync.cluster_size = cs; e->sync.n_clusters = grid / cs;
     e->pgrid = grid; e->pblock = block; e->psmem = bytes;
-    int gs = 1;
-    while (gs * gs < grid) ++gs;
-    e->sync.group_size = gs;
-    e->sync.n_groups = (grid + gs - 1) / gs;
+    return true;
+}
+
+static void choose_persistent(rsrl_engine* e) {
+    e->persistent = false;
+    e->pmode = e->cfg.weight_mode;
+    if (e->has_trace && e->cfg.weight_mode == RSRL_PER_ENV) return;  // per-env W + traces: per-step kernels
+    int dev = e->cfg.device, sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) return;
+    if (e->cfg.weight_mode == RSRL_PER_ENV) {
+        e->pblock = 128;
+        e->pgrid = (int)((e->N + e->pblock - 1) / e->pblock);
+        // every env's own W in shared memory (F*A x 128 columns) when at least two CTAs still fit on an SM
+        const size_t wbytes = (size_t)e->FA * e->pblock * e->rsz;
+        e->sync.pe_smem = wbytes <= 110 * 1024 ? 1 : 0;
+        e->psmem = e->sync.pe_smem ? wbytes : 0;
+        e->persistent = true;
+        return;
+    }
+    if (e->has_trace) e->pmode = kModeSharedTrace;
+    e->sync.debug_skip = getenv("RSRL_B200_DEBUG_SKIP") ? atoi(getenv("RSRL_B200_DEBUG_SKIP")) : 0;
+    int g0 = (int)((e->N + 127) / 128);
+    if (g0 > sms) g0 = sms;
+    // cluster size: 8 (portable maximum) packs 16 clusters = 128 CTAs on a B200 (8 GPCs of 16-20 SMs); RSRL_B200_CLUSTER overrides
+    int cs = getenv("RSRL_B200_CLUSTER") ? atoi(getenv("RSRL_B200_CLUSTER")) : 8;
+    if (cs < 1 || cs > kMaxClusterSize || (cs & (cs - 1))) cs = 8;
+    if (g0 == 1) cs = 1;
+    int grid = (g0 + cs - 1) / cs * cs;
+    if (!persistent_shape(e, grid, cs)) return;
+    if (grid > 1) {
+        // co-residency: shrink the grid to what the device can hold at once (the envs are re-split over fewer CTAs)
+        int maxc = 0;
+        StepArgs a;
+        memset(&a, 0, sizeof a);
+        PeerArgs pe;
+        memset(&pe, 0, sizeof pe);
+        cudaError_t ce = dispatch_persist(e->key, e->pmode, a, 0, e->sync, pe, grid, e->pblock, e->psmem, e->stream, &maxc);
+        if (ce != cudaSuccess) { cudaGetLastError(); return; }  // combination not built / cluster shape not launchable: per-step kernels
+        if (maxc < 1) return;
+        if (grid / cs > maxc) {
+            grid = maxc * cs;
+            if (!persistent_shape(e, grid, cs)) return;
+            ce = dispatch_persist(e->key, e->pmode, a, 0, e->sync, pe, grid, e->pblock, e->psmem, e->stream, &maxc);
+            if (ce != cudaSuccess || grid / cs > maxc) { cudaGetLastError(); return; }
+        }
+    }
     e->persistent = true;
 }
 
@@ -324,10 +356,10 @@ static StepArgs make_args(rsrl_engine* e) {
 }
 
 template <typename R>
-static cudaError_t launch_reduce(rsrl_engine* e, int n_blocks) {
+static cudaError_t launch_reduce(rsrl_engine* e, int n_blocks, bool to_dw) {
     const int threads = 128, blocks = (int)((e->FA + threads - 1) / threads);
     reduce_partials_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<const R*>(e->partials), n_blocks, (int)e->FA,
-                                                                  static_cast<R*>(e->W), e->world > 1 ? static_cast<R*>(e->dW) : nullptr);
+                                                                  static_cast<R*>(e->W), to_dw ? static_cast<R*>(e->dW) : nullptr);
     return cudaGetLastError();
 }
 template <typename R>
@@ -337,12 +369,22 @@ static cudaError_t launch_add(rsrl_engine* e) {
     return cudaGetLastError();
 }
 
+// The per-step kernels exchange dW with ncclAllReduce: that needs rsrl_engine_comm_init.  A peer-attached engine
+// (rsrl_engine_peer_attach) without a communicator can only run the persistent kernel.
+static int need_comm(const rsrl_engine* e) {
+    if (e->world > 1 && e->cfg.weight_mode == RSRL_SHARED && !e->comm)
+        return fail(RSRL_ECOMM, "this engine is peer-attached without an NCCL communicator: the per-step kernels (rsrl_engine_handle, "
+                                "shapes outside the persistent kernel) need rsrl_engine_comm_init");
+    return RSRL_OK;
+}
+
 // after a SHARED-mode fused launch: partials -> dW (-> allreduce) -> W
 static int finish_shared_step(rsrl_engine* e, int n_blocks) {
-    if (e->f4tc) CU_TRY(launch_f4tc_reduce(e->partials, n_blocks, (int)e->FA, e->W, e->world > 1 ? e->dW : nullptr, e->stream));
-    else CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks) : launch_reduce<double>(e, n_blocks));
+    const bool xch = e->world > 1 && e->comm != nullptr;
+    if (e->f4tc) CU_TRY(launch_f4tc_reduce(e->partials, n_blocks, (int)e->FA, e->W, xch ? e->dW : nullptr, e->stream));
+    else CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks, xch) : launch_reduce<double>(e, n_blocks, xch));
     e->launches += 1;
-    if (e->world > 1) {
+    if (xch) {
         ncclResult_t r = g_nccl.AllReduce(e->dW, e->dW, (size_t)e->FA, e->cfg.dtype == RSRL_F32 ? ncclFloat32 : ncclFloat64,
                                           ncclSum, e->comm, e->stream);
         if (r != ncclSuccess) return fail(RSRL_ECOMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
@@ -352,7 +394,7 @@ static int finish_shared_step(rsrl_engine* e, int n_blocks) {
     return RSRL_OK;
 }
 
-static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
+static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n, const int32_t* acts /* device: actions the dW pass reads */) {
     const bool f32 = e->cfg.dtype == RSRL_F32;
     cudaError_t ce;
     if (e->f4tc & 1) {
@@ -368,12 +410,12 @@ static int f4_step(rsrl_engine* e, const StepArgs& a, bool ext, int64_t n) {
     if (e->f4tc & 2) {
         const int64_t n_sub = (n + 31) / 32;
         nseg = (int)(n_sub < e->f4tc_dw_grid ? n_sub : e->f4tc_dw_grid);
-        CU_TRY(launch_f4tc_dw(e->cfg.domain, n, e->f4args.tabs, e->f4args.coef, e->actions, nseg, e->partials, e->counters, e->phase_prof ? e->phase_prof + (size_t)e->pgrid * 8 : nullptr, e->stream));
+        CU_TRY(launch_f4tc_dw(e->cfg.domain, n, e->f4args.tabs, e->f4args.coef, acts, nseg, e->partials, e->counters, e->phase_prof ? e->phase_prof + (size_t)e->pgrid * 8 : nullptr, e->stream));
     } else {
         nseg = e->f4_nseg;
         const int64_t max_seg = (n + 63) / 64;
         if (nseg > max_seg) nseg = (int)max_seg;
-        CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, e->actions, nseg, e->partials, e->stream));
+        CU_TRY((f32 ? launch_f4_dw_f32 : launch_f4_dw_f64)(e->cfg.domain, e->cfg.basis_order, n, e->f4args.from_states, e->f4args.coef, acts, nseg, e->partials, e->stream));
     }
     e->launches += e->f4tc ? 4 : 2;
     return finish_shared_step(e, nseg);
@@ -441,7 +483,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage1, e->sync.stage2, e->inbox, e->peer.stage3, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef, e->f4args.tabs, e->f4args.q, e->f4args.aux, e->f4args.next_states};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage, e->inbox, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef, e->f4args.tabs, e->f4args.q, e->f4args.aux, e->f4args.next_states};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -475,6 +517,10 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     e->has_trace = algo_has_trace(cfg->algo);
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
     e->epsilon = cfg->epsilon;
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete e; return fail(RSRL_ECUDA, std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(se)); }
+    }
     if (e->f4) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -523,7 +569,6 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
                         std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
         }                                                                                            \
     } while (0)
-    E_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     const size_t N = (size_t)e->N;
     E_TRY(cudaMalloc(&e->states, N * e->D * sizeof(double)));
     E_TRY(cudaMalloc(&e->actions, N * sizeof(int32_t)));
@@ -559,14 +604,12 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;       // reduce rows
         const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;                       // values per row
         const size_t nl = rows * (e->cfg.dtype == RSRL_F32 ? 1 : ndc);             // 16-byte LL lines per partial
-        e->sync1_bytes = (size_t)e->pgrid * nl * sizeof(uint4);
-        e->sync2_bytes = (size_t)2 * e->sync.n_groups * nl * sizeof(uint4);
-        e->stage3_bytes = 2 * nl * sizeof(uint4);
-        E_TRY(cudaMalloc(&e->sync.stage1, e->sync1_bytes));
-        e->inbox_bytes = (size_t)2 * kMaxRanks * e->FA * (e->rsz / 4) * sizeof(uint2);
+        e->stage_bytes = (size_t)2 * e->sync.n_clusters * nl * sizeof(uint4);
+        E_TRY(cudaMalloc(&e->sync.stage, e->stage_bytes));
+        E_TRY(cudaMemset(e->sync.stage, 0, e->stage_bytes));                       // epoch 0 is never published
+        e->inbox_bytes = (size_t)2 * kMaxRanks * e->sync.n_clusters * e->FA * (e->rsz / 4) * sizeof(uint2);
         E_TRY(cudaMalloc(&e->inbox, e->inbox_bytes));
-        E_TRY(cudaMalloc(&e->peer.stage3, e->stage3_bytes));
-        E_TRY(cudaMalloc(&e->sync.stage2, e->sync2_bytes));
+        E_TRY(cudaMemset(e->inbox, 0, e->inbox_bytes));
     }
     E_TRY(cudaMalloc(&e->counters, sizeof(Counters)));
     if (getenv("RSRL_B200_PHASE_PROFILE") && e->f4tc) e->pgrid = e->f4tc_env_grid;
@@ -605,15 +648,13 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     CU_TRY(cudaMemsetAsync(e->last_len, 0, N * sizeof(int32_t), st));
     CU_TRY(cudaMemsetAsync(e->len_hash, 0, N * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(e->counters, 0, sizeof(Counters), st));
-    if (e->sync.stage1) CU_TRY(cudaMemsetAsync(e->sync.stage1, 0, e->sync1_bytes, st));  // epoch 0 is never published
-    if (e->sync.stage2) CU_TRY(cudaMemsetAsync(e->sync.stage2, 0, e->sync2_bytes, st));
-    if (e->inbox) CU_TRY(cudaMemsetAsync(e->inbox, 0, e->inbox_bytes, st));
+    // the exchange mailboxes and their epoch (e->xepoch) live as long as the engine: resetting them could erase or
+    // alias a peer GPU's in-flight words (ranks reset without a barrier between them)
     if (e->tile) {
         CU_TRY(cudaMemsetAsync(e->targs.G, 0, e->tileG_bytes, st));
         CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
         e->tile_steps = 0;
     }
-    if (e->peer.stage3) CU_TRY(cudaMemsetAsync(e->peer.stage3, 0, e->stage3_bytes, st));
     e->t = 0;
     if (init_states) {
         CU_TRY(cudaMemcpyAsync(e->states, init_states, N * e->D * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -640,9 +681,10 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     if (k_steps < 0) return fail(RSRL_EINVAL, "k_steps < 0");
     CU_TRY(cudaSetDevice(e->cfg.device));
     if (e->f4) {
+        { int rc = need_comm(e); if (rc) return rc; }
         for (int64_t k = 0; k < k_steps; ++k) {
             StepArgs a = make_args(e);
-            int rc = f4_step(e, a, false, e->N);
+            int rc = f4_step(e, a, false, e->N, e->actions);
             if (rc) return rc;
             e->t += 1;
         }
@@ -654,7 +696,7 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
             e->targs.barrier_base = e->tile_steps;
-            if (e->targs.dense) CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), e->stream));  // launch-local targets
+            CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), e->stream));  // launch-local barrier targets (both kernels)
             auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;
             CU_TRY(fn(e->cfg.domain, e->AW, false, a, k, e->targs, e->pgrid, e->pblock, e->psmem, e->stream));
             e->launches += 1;
@@ -668,6 +710,7 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
         while (k_steps > 0) {
             const int k = (int)(k_steps < 65536 ? k_steps : 65536);
             StepArgs a = make_args(e);
+            e->sync.epoch_base = e->xepoch;
             cudaError_t ce = dispatch_persist(e->key, e->pmode, a, k, e->sync, e->peer, e->pgrid, e->pblock, e->psmem, e->stream);
             if (ce == cudaErrorCooperativeLaunchTooLarge) {  // cannot be co-resident here: per-step kernels instead
                 cudaGetLastError();
@@ -677,10 +720,12 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
             CU_TRY(ce);
             e->launches += 1;
             e->t += (uint64_t)k;
+            e->xepoch += (uint32_t)k;
             k_steps -= k;
         }
         return RSRL_OK;
     }
+    { int rc = need_comm(e); if (rc) return rc; }
     for (int64_t k = 0; k < k_steps; ++k) {
         StepArgs a = make_args(e);
         CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream));
@@ -874,6 +919,7 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
     if ((e->has_trace || e->cfg.weight_mode == RSRL_PER_ENV) && n != e->N)
         return fail(RSRL_EINVAL, "per-env traces / weights: n must equal n_envs (transition i belongs to agent i)");
     if (n > e->N) return fail(RSRL_EINVAL, "n exceeds n_envs");
+    { int rc = need_comm(e); if (rc) return rc; }
     for (int64_t i = 0; i < n; ++i)
         if (actions[i] < 0 || actions[i] >= e->A) return fail(RSRL_EINVAL, "action out of range");
     CU_TRY(cudaSetDevice(e->cfg.device));
@@ -892,13 +938,11 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
     a.ext_from = dfrom.as<double>(); a.ext_to = dto.as<double>(); a.ext_actions = dact.as<int32_t>();
     a.ext_rewards = drew.as<double>(); a.ext_term = dterm.as<uint8_t>();
     if (e->f4) {
-        // the dW pass reads the caller's actions from the engine's action buffer
-        CU_TRY(cudaMemcpyAsync(e->actions, actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        int rc = f4_step(e, a, true, n);
+        int rc = f4_step(e, a, true, n, dact.as<int32_t>());  // the dW pass reads the caller's actions (the engine's own stay untouched)
         if (rc) return rc;
     } else if (e->tile) {
         e->targs.barrier_base = e->tile_steps;
-        if (e->targs.dense) CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(e->targs.barrier, 0, sizeof(unsigned long long), st));
         int g2 = (int)((n + 127) / 128);
         if (g2 > e->pgrid) g2 = e->pgrid;
         auto fn = e->cfg.dtype == RSRL_F32 ? launch_tile_persist_f32 : launch_tile_persist_f64;
@@ -925,6 +969,45 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
         CU_TRY(cudaMemcpyAsync(td_out, e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(st));
+    return RSRL_OK;
+}
+
+// ---- introspection used by the parity tests ----
+int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[16]) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    memset(out, 0, 16 * sizeof(int32_t));
+    out[0] = e->persistent ? 1 : 0; out[1] = e->pmode; out[2] = e->pgrid; out[3] = e->sync.cluster_size; out[4] = e->sync.n_clusters;
+    out[5] = e->pblock; out[6] = e->sync.lpr; out[7] = e->sync.lpg; out[8] = e->sync.seg_len; out[9] = e->sync.pe_smem;
+    out[10] = e->world; out[11] = e->rank; out[12] = e->peers_attached ? 1 : 0; out[13] = (int32_t)e->psmem;
+    out[14] = e->tile ? 1 : 0; out[15] = e->f4 ? (1 + e->f4tc) : 0;
+    return RSRL_OK;
+}
+
+static __global__ void math_probe_kernel(int fn, int64_t n, const double* __restrict__ x, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    float sf, cf;
+    switch (fn) {
+        case 0: out[i] = cos64(x[i]); break;
+        case 1: sincos64(x[i], &s, &c); out[i] = s; break;
+        case 2: sincospi32((float)x[i], &sf, &cf); out[i] = (double)sf; break;
+        case 3: sincospi32((float)x[i], &sf, &cf); out[i] = (double)cf; break;
+        default: out[i] = (double)exp32((float)x[i]); break;
+    }
+}
+
+int rsrl_math_probe(int32_t fn, int64_t n, const double* x, double* out) {
+    if (fn < 0 || fn > 4 || n <= 0 || !x || !out) return fail(RSRL_EINVAL, "bad argument");
+    int rc = need_device();
+    if (rc) return rc;
+    DevBuf dx, dout;
+    CU_TRY(dx.alloc(n * sizeof(double))); CU_TRY(dout.alloc(n * sizeof(double)));
+    CU_TRY(cudaMemcpy(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    math_probe_kernel<<<blocks, threads>>>(fn, n, dx.as<double>(), dout.as<double>());
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     return RSRL_OK;
 }
 

@@ -7,8 +7,7 @@
 // thread, the Fourier features are generated from per-dimension sin/cos tables
 // (Kronecker structure) and never touch memory.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "hostdev.h"
 #include "../../include/rsrl_b200.h"
 
 namespace rsrl {
@@ -16,16 +15,12 @@ namespace rsrl {
 // ---------------------------------------------------------------------------
 // scalar helpers
 // ---------------------------------------------------------------------------
-// f64 physics: explicit round-to-nearest ops so that nvcc does not contract a*b+c into
-// DFMA — the reference (Rust, no FMA contraction) rounds after every operation.
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// f64 physics: explicit round-to-nearest ops (hostdev.h: dmul / dadd / dsub / ddiv) so that nvcc does not contract a*b+c
+// into DFMA — the reference (Rust, no FMA contraction) rounds after every operation.
 // clip!(lb, x, ub) = lb.max(ub.min(x))  (rsrl_domains/src/macros.rs:20-24); fmin/fmax drop NaN like Rust
-__device__ __forceinline__ double dclip(double lb, double x, double ub) { return fmax(lb, fmin(ub, x)); }
+__host__ __device__ __forceinline__ double dclip(double lb, double x, double ub) { return fmax(lb, fmin(ub, x)); }
 // wrap!(lb, x, ub)  (macros.rs:3-18)
-__device__ __forceinline__ double dwrap(double lb, double x, double ub) {
+__host__ __device__ __forceinline__ double dwrap(double lb, double x, double ub) {
     double nx = x;
     const double diff = dsub(ub, lb);
     while (nx > ub) nx = dsub(nx, diff);
@@ -35,29 +30,134 @@ __device__ __forceinline__ double dwrap(double lb, double x, double ub) {
 
 #define RSRL_PI 3.14159265358979323846264338327950288
 
+// ---------------------------------------------------------------------------
+// rsrl math: the elementary functions of the hot path, written out so that the GPU and the host build
+// (oracle/oracle32.cpp) round identically.  Accuracy (tests/test_arith32.py, against mpmath): sin64 / cos64
+// < 1 ulp for |x| < 2^20 (3-term Cody-Waite reduction with FMA + the classic degree-13/14 minimax kernels
+// on [-pi/4, pi/4]); sincospi32 < 1 ulp (reduction x - rint(2x)/2 is exact); exp32 < 1 ulp.
+// Outside those ranges (never reached by the bounded domains) the platform libm is used.
+// ---------------------------------------------------------------------------
+// x = n*pi/2 + (r + lo), |r| <= pi/4 + eps, |lo| < ulp(r); returns n mod 4
+__host__ __device__ __forceinline__ int rem_pio2_64(double x, double& r, double& lo) {
+    const double n = rint(dmul(x, 0.63661977236758138));          // 2/pi
+    const double r1 = dfma(n, -1.5707963267948966, x);            // exact: x and n*P1 cancel to <= 53 bits
+    r = dfma(n, -6.123233995736766e-17, r1);
+    lo = dfma(n, -6.123233995736766e-17, dsub(r1, r));            // the rounding error of r ...
+    lo = dfma(n, -1.4973849048591698e-33, lo);                    // ... and the third part of pi/2
+    return (int)n & 3;
+}
+__host__ __device__ __forceinline__ double sin_kernel64(double r, double lo) {  // sin(r + lo)
+    const double z = dmul(r, r);
+    double p = 1.58969099521155010221e-10;
+    p = dfma(p, z, -2.50507602534068634195e-08);
+    p = dfma(p, z, 2.75573137070700676789e-06);
+    p = dfma(p, z, -1.98412698298579493134e-04);
+    p = dfma(p, z, 8.33333333332248946124e-03);
+    p = dfma(p, z, -1.66666666666666324348e-01);
+    const double corr = dfma(dmul(r, z), p, dmul(lo, dfma(z, -0.5, 1.0)));  // r^3 p(z) + lo cos(r)
+    return dadd(r, corr);
+}
+__host__ __device__ __forceinline__ double cos_kernel64(double r, double lo) {  // cos(r + lo)
+    const double z = dmul(r, r);
+    double p = -1.13596475577881948265e-11;
+    p = dfma(p, z, 2.08757232129817482790e-09);
+    p = dfma(p, z, -2.75573143513906633035e-07);
+    p = dfma(p, z, 2.48015872894767294178e-05);
+    p = dfma(p, z, -1.38888888888741095749e-03);
+    p = dfma(p, z, 4.16666666666666019037e-02);
+    const double h = dfma(z, -0.5, 1.0);                           // 1 - z/2 and its rounding error e
+    const double e = dfma(z, -0.5, dsub(1.0, h));
+    return dadd(h, dadd(e, dfma(dmul(z, z), p, -dmul(r, lo))));    // + z^2 p(z) - lo sin(r)
+}
+__host__ __device__ __forceinline__ void sincos64(double x, double* s, double* c) {
+    if (!(fabs(x) < 1048576.0)) { *s = ::sin(x); *c = ::cos(x); return; }  // out of the pinned range (incl. NaN / Inf)
+    double r, lo;
+    const int q = rem_pio2_64(x, r, lo);
+    const double sk = sin_kernel64(r, lo), ck = cos_kernel64(r, lo);
+    const double sv = (q & 1) ? ck : sk, cv = (q & 1) ? sk : ck;
+    *s = (q & 2) ? -sv : sv;
+    *c = ((q + 1) & 2) ? -cv : cv;
+}
+__host__ __device__ __forceinline__ double cos64(double x) {
+    if (!(fabs(x) < 1048576.0)) return ::cos(x);
+    double r, lo;
+    const int q = rem_pio2_64(x, r, lo);
+    const double v = (q & 1) ? sin_kernel64(r, lo) : cos_kernel64(r, lo);
+    return ((q + 1) & 2) ? -v : v;
+}
+
+// sin(pi x), cos(pi x) in fp32.  t = rint(2x); r = x - t/2 is exact; |r| <= 1/4.
+__host__ __device__ __forceinline__ void sincospi32(float x, float* s, float* c) {
+    if (!(fabsf(x) < 4194304.0f)) x = fmul(x, 0.0f);  // huge: an even integer for every such float; NaN / Inf -> NaN
+    const float t = rintf(fadd(x, x));
+    const float r = ffma(t, -0.5f, x);
+    const float z = fmul(r, r);
+    float ps = -0.5890144109725952f;
+    ps = ffma(ps, z, 2.5497612953186035f);
+    ps = ffma(ps, z, -5.167707920074463f);
+    // pi r = r * pi_hi + r * pi_lo, then the cubic and higher terms
+    const float sk = ffma(r, 3.1415927410125732f, ffma(r, -8.742277657347586e-08f, fmul(fmul(r, z), ps)));
+    float pc = 0.23136425018310547f;
+    pc = ffma(pc, z, -1.3350505828857422f);
+    pc = ffma(pc, z, 4.0587077140808105f);
+    pc = ffma(pc, z, -4.934802055358887f);
+    const float ck = ffma(pc, z, 1.0f);
+    const int q = (int)t & 3;
+    const float sv = (q & 1) ? ck : sk, cv = (q & 1) ? sk : ck;
+    *s = (q & 2) ? -sv : sv;
+    *c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// e^x in fp32 (Softmax policy)
+__host__ __device__ __forceinline__ float exp32(float x) {
+    if (!(x <= 88.72283935546875f)) return x > 0.0f ? bits_to_float(0x7f800000u) : x;  // +Inf; NaN stays NaN
+    if (x < -103.97208404541016f) return 0.0f;
+    const float n = rintf(fmul(x, 1.4426950216293335f));
+    float r = ffma(n, -0.693145751953125f, x);        // ln2 high part (trailing zero bits: n * hi is exact)
+    r = ffma(n, -1.4286068203094172e-06f, r);
+    float p = 0.0013814615085721016f;
+    p = ffma(p, r, 0.008368710055947304f);
+    p = ffma(p, r, 0.04166838899254799f);
+    p = ffma(p, r, 0.1666652113199234f);
+    p = ffma(p, r, 0.4999999403953552f);
+    const float e = fadd(ffma(fmul(r, r), p, r), 1.0f);
+    const int ni = (int)n, n1 = ni >> 1, n2 = ni - n1;  // two exact power-of-two scalings: denormal results round once
+    return fmul(fmul(e, bits_to_float((uint32_t)(n1 + 127) << 23)), bits_to_float((uint32_t)(n2 + 127) << 23));
+}
+
 template <typename R> struct RealOps;
 template <> struct RealOps<float> {
-    __device__ __forceinline__ static void sincospi(float x, float* s, float* c) { sincospif(x, s, c); }
-    __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    __host__ __device__ __forceinline__ static void sincospi(float x, float* s, float* c) { sincospi32(x, s, c); }
+    __host__ __device__ __forceinline__ static float fma(float a, float b, float c) { return ffma(a, b, c); }
+    // Q accumulation q + phi * w: fused in fp32
+    __host__ __device__ __forceinline__ static float mac(float a, float b, float c) { return ffma(a, b, c); }
     // w + c*x with the product rounded first (the reference's SGD `w = w + (lr*err) * phi` is not fused)
-    __device__ __forceinline__ static float mul_add_unfused(float c, float x, float w) { return __fadd_rn(w, __fmul_rn(c, x)); }
-    __device__ __forceinline__ static float abs(float a) { return fabsf(a); }
-    __device__ __forceinline__ static float lowest() { return -3.402823466e+38f; }  // magnitude only matters vs 1e-7
-    __device__ __forceinline__ static float clamp1(float x) { return fmaxf(-1.0f, fminf(1.0f, x)); }
-    __device__ __forceinline__ static float exp(float x) { return expf(x); }
-    __device__ __forceinline__ static float max_nan(float a, float b) { return fmaxf(a, b); }  // f64::max: drops NaN
-    __device__ __forceinline__ static float min_max(float x) { return fminf(x, 3.402823466e+38f); }
+    __host__ __device__ __forceinline__ static float mul_add_unfused(float c, float x, float w) { return fadd(w, fmul(c, x)); }
+    __host__ __device__ __forceinline__ static float abs(float a) { return fabsf(a); }
+    __host__ __device__ __forceinline__ static float lowest() { return -3.402823466e+38f; }  // magnitude only matters vs 1e-7
+    __host__ __device__ __forceinline__ static float clamp1(float x) { return fmaxf(-1.0f, fminf(1.0f, x)); }
+    __host__ __device__ __forceinline__ static float exp(float x) { return exp32(x); }
+    __host__ __device__ __forceinline__ static float max_nan(float a, float b) { return fmaxf(a, b); }  // f64::max: drops NaN
+    __host__ __device__ __forceinline__ static float min_max(float x) { return fminf(x, 3.402823466e+38f); }
 };
 template <> struct RealOps<double> {
-    __device__ __forceinline__ static void sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
-    __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
-    __device__ __forceinline__ static double mul_add_unfused(double c, double x, double w) { return __dadd_rn(w, __dmul_rn(c, x)); }
-    __device__ __forceinline__ static double abs(double a) { return fabs(a); }
-    __device__ __forceinline__ static double lowest() { return -1.7976931348623157e+308; }  // f64::MIN
-    __device__ __forceinline__ static double clamp1(double x) { return fmax(-1.0, fmin(1.0, x)); }
-    __device__ __forceinline__ static double exp(double x) { return ::exp(x); }
-    __device__ __forceinline__ static double max_nan(double a, double b) { return fmax(a, b); }
-    __device__ __forceinline__ static double min_max(double x) { return fmin(x, 1.7976931348623157e+308); }
+    __host__ __device__ __forceinline__ static void sincospi(double x, double* s, double* c) {
+#if RSRL_HOST_BUILD
+        *s = ::sin(RSRL_PI * x); *c = ::cos(RSRL_PI * x);  // the host build only instantiates fp32 (oracle32)
+#else
+        ::sincospi(x, s, c);
+#endif
+    }
+    __host__ __device__ __forceinline__ static double fma(double a, double b, double c) { return dfma(a, b, c); }
+    // dtype f64 is the reference's arithmetic: q + phi * w rounds the product first (ndarray dot / the oracle do not fuse)
+    __host__ __device__ __forceinline__ static double mac(double a, double b, double c) { return dadd(c, dmul(a, b)); }
+    __host__ __device__ __forceinline__ static double mul_add_unfused(double c, double x, double w) { return dadd(w, dmul(c, x)); }
+    __host__ __device__ __forceinline__ static double abs(double a) { return fabs(a); }
+    __host__ __device__ __forceinline__ static double lowest() { return -1.7976931348623157e+308; }  // f64::MIN
+    __host__ __device__ __forceinline__ static double clamp1(double x) { return fmax(-1.0, fmin(1.0, x)); }
+    __host__ __device__ __forceinline__ static double exp(double x) { return ::exp(x); }
+    __host__ __device__ __forceinline__ static double max_nan(double a, double b) { return fmax(a, b); }
+    __host__ __device__ __forceinline__ static double min_max(double x) { return fmin(x, 1.7976931348623157e+308); }
 };
 
 // ---------------------------------------------------------------------------
@@ -66,11 +166,11 @@ template <> struct RealOps<double> {
 // ---------------------------------------------------------------------------
 enum : uint32_t { STREAM_INIT = 0, STREAM_BEHAVIOUR = 1, STREAM_TARGET = 2 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        const uint32_t hi0 = umulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = umulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
         k.x += 0x9E3779B9u;
         k.y += 0xBB67AE85u;
@@ -78,12 +178,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-__device__ __forceinline__ uint4 draw4(uint64_t seed, uint64_t env, uint64_t draw, uint32_t stream) {
+__host__ __device__ __forceinline__ uint4 draw4(uint64_t seed, uint64_t env, uint64_t draw, uint32_t stream) {
     return philox4x32_10(make_uint4((uint32_t)env, (uint32_t)draw, (uint32_t)(draw >> 32), stream),
                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-__device__ __forceinline__ uint32_t word(const uint4& r, int d) { return d == 0 ? r.x : d == 1 ? r.y : d == 2 ? r.z : r.w; }
+__host__ __device__ __forceinline__ uint32_t word(const uint4& r, int d) { return d == 0 ? r.x : d == 1 ? r.y : d == 2 ? r.z : r.w; }
 
 // ---------------------------------------------------------------------------
 // Domains: one env step in registers.  `Domain::step` of rsrl_domains/src/lib.rs:434.
@@ -96,11 +196,11 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
     __host__ __device__ static constexpr double lo(int d) { return d == 0 ? -1.2 : -0.07; }
     __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 0.6 : 0.07; }
     __host__ __device__ static constexpr double start(int d) { return d == 0 ? -0.5 : 0.0; }
-    __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
+    __host__ __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
     template <bool ROLLED = false>
-    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+    __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double a = (double)(action - 1);                                        // ALL_ACTIONS = [-1, 0, 1]
-        const double dv = dadd(dmul(0.001, a), dmul(-0.0025, cos(dmul(3.0, s[0]))));  // :58
+        const double dv = dadd(dmul(0.001, a), dmul(-0.0025, cos64(dmul(3.0, s[0]))));  // :58
         s[1] = dclip(-0.07, dadd(s[1], dv), 0.07);                                    // :63
         s[0] = dclip(-1.2, dadd(s[0], s[1]), 0.6);                                    // :64 (uses the new v)
         terminal = s[0] >= 0.6;                                                       // :77
@@ -112,7 +212,7 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
 // ROLLED = true keeps one copy of the gradient code (a 4-trip loop, same operations in the same order, bit-identical
 // results): used by kernels whose instruction footprint matters (f4tc.cuh).
 template <bool ROLLED = false, class Grad>
-__device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
+__host__ __device__ __forceinline__ void runge_kutta4(Grad f, double* y, double dx) {
     if (ROLLED) {
         double k[4], tmp[4], sum[4];
 #pragma unroll
@@ -158,17 +258,17 @@ template <> struct Domain<RSRL_CART_POLE> {
     __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 2.4 : d == 1 ? 6.0 : d == 2 ? TWELVE_DEGREES : 2.0; }
     __host__ __device__ static constexpr double lo(int d) { return -hi(d); }
     __host__ __device__ static constexpr double start(int) { return 0.0; }
-    __device__ __forceinline__ static bool is_terminal(const double* s) {  // :83-97
+    __host__ __device__ __forceinline__ static bool is_terminal(const double* s) {  // :83-97
         return s[0] <= -2.4 || s[0] >= 2.4 || s[2] <= -TWELVE_DEGREES || s[2] >= TWELVE_DEGREES;
     }
     template <bool ROLLED = false>
-    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+    __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double force = action == 0 ? -10.0 : 10.0;  // ALL_ACTIONS :26
         constexpr double POLE_MOMENT = 0.5 * 0.1, TOTAL_MASS = 1.0 + 0.1, FOUR_THIRDS = 4.0 / 3.0, G = 9.8;
         auto grad = [force](const double* b, double* out) {  // :52-72
             const double dx = b[1], theta = b[2], dtheta = b[3];
             double sin_t, cos_t;
-            sincos(theta, &sin_t, &cos_t);
+            sincos64(theta, &sin_t, &cos_t);
             const double z = ddiv(dadd(force, dmul(dmul(dmul(POLE_MOMENT, dtheta), dtheta), sin_t)), TOTAL_MASS);
             const double numer = dsub(dmul(G, sin_t), dmul(cos_t, z));
             const double denom = dsub(dmul(FOUR_THIRDS, 0.5), dmul(dmul(POLE_MOMENT, cos_t), cos_t));
@@ -194,27 +294,27 @@ template <> struct Domain<RSRL_ACROBOT> {
     __host__ __device__ static constexpr double hi(int d) { return d < 2 ? RSRL_PI : d == 2 ? 4.0 * RSRL_PI : 9.0 * RSRL_PI; }
     __host__ __device__ static constexpr double lo(int d) { return -hi(d); }
     __host__ __device__ static constexpr double start(int) { return 0.0; }
-    __device__ __forceinline__ static bool is_terminal(const double* s) {  // :56-58
-        return dadd(cos(s[0]), cos(dadd(s[0], s[1]))) < -1.0;
+    __host__ __device__ __forceinline__ static bool is_terminal(const double* s) {  // :56-58
+        return dadd(cos64(s[0]), cos64(dadd(s[0], s[1]))) < -1.0;
     }
     template <bool ROLLED = false>
-    __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+    __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double torque = (double)(action - 1);  // ALL_ACTIONS = [-1, 0, 1] :36
         constexpr double G = 9.8, PI_OVER_2 = RSRL_PI / 2.0;
         auto grad = [torque](const double* b, double* out) {  // :81-108 (M1=M2=L1=1, LC1=LC2=0.5, I1=I2=1)
             const double theta1 = b[0], theta2 = b[1], dtheta1 = b[2], dtheta2 = b[3];
             double sin_t2, cos_t2;
-            sincos(theta2, &sin_t2, &cos_t2);
+            sincos64(theta2, &sin_t2, &cos_t2);
             // d1 = M1*LC1*LC1 + M2*(L1*L1 + LC2*LC2 + 2*L1*LC2*cos_t2) + I1 + I2
             const double d1 = dadd(dadd(dadd(0.25, dmul(1.0, dadd(dadd(1.0, 0.25), dmul(1.0, cos_t2)))), 1.0), 1.0);
             // d2 = M2*(LC2*LC2 + L1*LC2*cos_t2) + I2
             const double d2 = dadd(dmul(1.0, dadd(0.25, dmul(0.5, cos_t2))), 1.0);
             // phi2 = M2*LC2*G*cos(theta1 + theta2 - PI/2)
-            const double phi2 = dmul(dmul(0.5, G), cos(dsub(dadd(theta1, theta2), PI_OVER_2)));
+            const double phi2 = dmul(dmul(0.5, G), cos64(dsub(dadd(theta1, theta2), PI_OVER_2)));
             // phi1 = -1*L1*LC2*dth2*dth2*sin_t2 - 2*M2*L1*LC2*dth2*dth1*sin_t2 + (M1*LC1 + M2*L1)*G*cos(th1 - PI/2) + phi2
             const double t1 = dmul(dmul(dmul(-0.5, dtheta2), dtheta2), sin_t2);
             const double t2 = dmul(dmul(dmul(1.0, dtheta2), dtheta1), sin_t2);  // 2.0*1*1*0.5 = 1.0 exactly
-            const double t3 = dmul(dmul(1.5, G), cos(dsub(theta1, PI_OVER_2)));
+            const double t3 = dmul(dmul(1.5, G), cos64(dsub(theta1, PI_OVER_2)));
             const double phi1 = dadd(dadd(dsub(t1, t2), t3), phi2);
             out[0] = dtheta1;
             out[1] = dtheta2;
@@ -237,7 +337,7 @@ template <> struct Domain<RSRL_ACROBOT> {
 
 // start state of the episode beginning at batched step t (Domain::default() or U[lo,hi) from Philox)
 template <class Dom>
-__device__ __forceinline__ void fresh_state(double* s, int init_mode, const double* init_lo, const double* init_hi,
+__host__ __device__ __forceinline__ void fresh_state(double* s, int init_mode, const double* init_lo, const double* init_hi,
                                             uint64_t seed, uint64_t g, uint64_t t) {
     if (init_mode == RSRL_INIT_DEFAULT) {
 #pragma unroll
@@ -266,7 +366,7 @@ struct GridTables {
 };
 
 template <typename R, class Dom, int P, int BASIS>
-__device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom::D, P, BASIS>& t) {
+__host__ __device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom::D, P, BASIS>& t) {
     using O = RealOps<R>;
 #pragma unroll
     for (int d = 0; d < Dom::D; ++d) {
@@ -304,7 +404,7 @@ struct GridBasis {
 
     // calls f(k, phi_k) for k = 0..F-1 in feature order; fully unrolled => k is a compile-time constant
     template <class Fn>
-    __device__ __forceinline__ static void for_each(const Tab& t, Fn f) {
+    __host__ __device__ __forceinline__ static void for_each(const Tab& t, Fn f) {
         using O = RealOps<R>;
         if (D == 2) {
 #pragma unroll
@@ -359,7 +459,7 @@ struct GridBasis {
         }
     }
 
-    __device__ __forceinline__ static void cmul(const Tab& t, int d0, int c0, int d1, int c1, R& re, R& im) {
+    __host__ __device__ __forceinline__ static void cmul(const Tab& t, int d0, int c0, int d1, int c1, R& re, R& im) {
         using O = RealOps<R>;
         const R a = c0 == 0 ? (R)1 : t.c[d0][c0 - 1], b = (c0 == 0 || BASIS != RSRL_FOURIER) ? (R)0 : t.s[d0][c0 - 1];
         if (c1 == 0) { re = a; im = b; return; }
@@ -368,7 +468,7 @@ struct GridBasis {
             im = O::fma(a, t.s[d1][c1 - 1], b * t.c[d1][c1 - 1]);
         } else { re = a * t.c[d1][c1 - 1]; im = (R)0; }
     }
-    __device__ __forceinline__ static void cmul_acc(const Tab& t, R a, R b, int d1, int c1, R& re, R& im) {
+    __host__ __device__ __forceinline__ static void cmul_acc(const Tab& t, R a, R b, int d1, int c1, R& re, R& im) {
         using O = RealOps<R>;
         if (c1 == 0) { re = a; im = b; return; }
         if (BASIS == RSRL_FOURIER) {
@@ -394,7 +494,7 @@ struct TileParams {
     int n_tilings, tiles_per_dim, memory_mask;
 };
 
-__device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* coord, int D) {
+__host__ __device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* coord, int D) {
     uint32_t h = (tiling + 1u) * 0x9E3779B1u;
     for (int d = 0; d < D; ++d) h = (h ^ (uint32_t)coord[d]) * 0x85EBCA6Bu;
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -403,7 +503,7 @@ __device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* co
 
 // TMAX: compile-time bound of the tiling loops (>= tp.n_tilings); 8 halves the unrolled hash / dedup code of 8-tiling configs
 template <class Dom, int TMAX = kMaxTilings>
-__device__ __forceinline__ void tile_prepare(const double* st, const TileParams& tp, TileTab& tab) {
+__host__ __device__ __forceinline__ void tile_prepare(const double* st, const TileParams& tp, TileTab& tab) {
     int32_t q[Dom::D];
 #pragma unroll
     for (int d = 0; d < Dom::D; ++d) {
@@ -436,7 +536,7 @@ __device__ __forceinline__ void tile_prepare(const double* st, const TileParams&
 // utils.rs:6-21 argmaxima: returns the tie set as a bit mask; a value within 1e-7 of `max` joins
 // without raising `max`.
 template <typename R, int A>
-__device__ __forceinline__ uint32_t argmaxima(const R* q, int& count) {
+__host__ __device__ __forceinline__ uint32_t argmaxima(const R* q, int& count) {
     using O = RealOps<R>;
     R mx = O::lowest();
     uint32_t mask = 0;
@@ -451,7 +551,7 @@ __device__ __forceinline__ uint32_t argmaxima(const R* q, int& count) {
 
 // core.rs:96-105 find_max: exact compare, the LAST maximal index wins, NaN replaces the accumulator
 template <typename R, int A>
-__device__ __forceinline__ int find_max(const R* q, R& mx) {
+__host__ __device__ __forceinline__ int find_max(const R* q, R& mx) {
     int idx = 0;
     mx = q[0];
 #pragma unroll
@@ -461,7 +561,7 @@ __device__ __forceinline__ int find_max(const R* q, R& mx) {
 
 // utils.rs:23-34 argmax_first: new best only if y - x > 1e-7, first wins
 template <typename R, int A>
-__device__ __forceinline__ int argmax_first(const R* q) {
+__host__ __device__ __forceinline__ int argmax_first(const R* q) {
     using O = RealOps<R>;
     int idx = 0;
     R x = O::lowest();
@@ -470,9 +570,9 @@ __device__ __forceinline__ int argmax_first(const R* q) {
     return idx;
 }
 
-__device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) {
+__host__ __device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) {
     for (int i = 0; i < n; ++i) mask &= mask - 1;
-    return __ffs(mask) - 1;
+    return ffs32(mask) - 1;
 }
 
 struct PolicyParams {
@@ -485,7 +585,7 @@ struct PolicyParams {
 
 // softmax.rs:15-36 softmax_stable: c = fold(NAN, f64::max); v_i = exp((q_i - c) / tau); p_i = min(v_i / sum v, MAX)
 template <typename R, int A>
-__device__ __forceinline__ void softmax_probs(R tau, const R* q, R* p) {
+__host__ __device__ __forceinline__ void softmax_probs(R tau, const R* q, R* p) {
     using O = RealOps<R>;
     R c = q[0];
 #pragma unroll
@@ -500,7 +600,7 @@ __device__ __forceinline__ void softmax_probs(R tau, const R* q, R* p) {
 // Policy::sample — greedy.rs:77-81 (argmax_choose_rng: RNG only on ties), epsilon_greedy.rs:74-80,
 // random.rs:43-45.  rnd.x -> gen_bool(eps), rnd.y -> Uniform(0, A), rnd.z -> choose among maxima.
 template <typename R, int A>
-__device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, uint64_t g, uint64_t draw,
+__host__ __device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, uint64_t g, uint64_t draw,
                                              uint32_t stream, bool& nonfinite) {
     if (p.policy == RSRL_SOFTMAX) {
         // policies/mod.rs:46-61 sample_probs_with_rng: r = rng.gen::<f64>() (53 bits: rnd.x high, rnd.y low);
@@ -520,24 +620,24 @@ __device__ __forceinline__ int policy_sample(const PolicyParams& p, const R* q, 
     if (p.policy != RSRL_GREEDY) {
         const uint4 r = draw4(p.seed, g, draw, stream);
         const bool explore = p.policy == RSRL_RANDOM || p.eps_always || r.x < p.eps_thresh;
-        if (explore) return (int)__umulhi(r.y, (uint32_t)A);
+        if (explore) return (int)umulhi32(r.y, (uint32_t)A);
         int cnt;
         const uint32_t mask = argmaxima<R, A>(q, cnt);
         if (cnt == 0) { nonfinite = true; return 0; }
-        if (cnt == 1) return __ffs(mask) - 1;
-        return nth_set_bit(mask, (int)__umulhi(r.z, (uint32_t)cnt));
+        if (cnt == 1) return ffs32(mask) - 1;
+        return nth_set_bit(mask, (int)umulhi32(r.z, (uint32_t)cnt));
     }
     int cnt;
     const uint32_t mask = argmaxima<R, A>(q, cnt);
     if (cnt == 0) { nonfinite = true; return 0; }
-    if (cnt == 1) return __ffs(mask) - 1;
+    if (cnt == 1) return ffs32(mask) - 1;
     const uint4 r = draw4(p.seed, g, draw, stream);  // rare: only on ties
-    return nth_set_bit(mask, (int)__umulhi(r.z, (uint32_t)cnt));
+    return nth_set_bit(mask, (int)umulhi32(r.z, (uint32_t)cnt));
 }
 
 // Function<(S,)>::evaluate of the policy (greedy.rs:30-44, epsilon_greedy.rs:38-45)
 template <typename R, int A>
-__device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p) {
+__host__ __device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p) {
     if (policy == RSRL_SOFTMAX) { softmax_probs<R, A>(eps, q, p); return; }  // eps carries tau
     if (policy == RSRL_RANDOM) {
 #pragma unroll
@@ -558,7 +658,7 @@ __device__ __forceinline__ void policy_probs(int policy, R eps, const R* q, R* p
 
 // Policy::mode — greedy.rs:83 find_max; softmax.rs:141 argmax_first over the probabilities
 template <typename R, int A>
-__device__ __forceinline__ int policy_mode(int policy, R tau, const R* q) {
+__host__ __device__ __forceinline__ int policy_mode(int policy, R tau, const R* q) {
     if (policy == RSRL_SOFTMAX) {
         R p[A];
         softmax_probs<R, A>(tau, q, p);
@@ -570,8 +670,8 @@ __device__ __forceinline__ int policy_mode(int policy, R tau, const R* q) {
 
 // traces.rs:196-240
 template <typename R>
-__device__ __forceinline__ R trace_rule(int rule, R rate, R z, R grad) {
-    const R v = RealOps<R>::fma(rate, z, grad);
+__host__ __device__ __forceinline__ R trace_rule(int rule, R rate, R z, R grad) {
+    const R v = RealOps<R>::mac(rate, z, grad);  // traces.rs:200,218,238 `rate * x + y`: unfused in f64 (the reference's ops), fused in fp32
     return rule == RSRL_TRACE_REPLACE ? RealOps<R>::clamp1(v) : v;
 }
 

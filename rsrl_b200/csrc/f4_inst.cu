@@ -12,11 +12,14 @@ typedef RSRL_REAL R;
 template <int DOM, int P, bool EXT>
 static cudaError_t env_one(const StepArgs& a, const F4Args& fa, int grid, int block, size_t smem, cudaStream_t st) {
     auto kern = f4_env_kernel<R, DOM, RSRL_FOURIER, P, Domain<DOM>::A, EXT>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};  // the opt-in is a per-device attribute of the function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     kern<<<grid, block, smem, st>>>(a, fa);
     return cudaGetLastError();

@@ -9,7 +9,10 @@ template <int DOM, int PHASE, bool EXT>
 static cudaError_t q_one(const StepArgs& a, const F4Args& fa, int n_tiles, int grid, cudaStream_t st) {
     auto kern = f4tc_q_kernel<DOM, PHASE, EXT>;
     constexpr size_t smem = F4tcEnvSmem<Domain<DOM>::A>::bytes;
-    static bool configured = false;
+    static bool configured_v[64] = {false};  // per device: the opt-in is a per-device attribute of the function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_v[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -40,7 +43,10 @@ static cudaError_t dw_one(int64_t n, const float* tabs, const void* coef, const 
                           Counters* counters, long long* prof, cudaStream_t st) {
     auto kern = f4tc_dw_kernel<DOM>;
     constexpr size_t smem = F4tcDwSmem<Domain<DOM>::A>::bytes;
-    static bool configured = false;
+    static bool configured_v[64] = {false};  // per device: the opt-in is a per-device attribute of the function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_v[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -112,11 +112,11 @@ __global__ void __launch_bounds__(128) f4_env_kernel(const StepArgs a, const F4A
             const vec_t v0 = p[0];
             if (Vec16<R>::N == 4) {
 #pragma unroll
-                for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, vget(v0, c), q[c]);
+                for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, vget(v0, c), q[c]);
             } else {
                 const vec_t v1 = AW > 2 ? p[1] : v0;
 #pragma unroll
-                for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, c < 2 ? vget(v0, c) : vget(v1, c - 2), q[c]);
+                for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, c < 2 ? vget(v0, c) : vget(v1, c - 2), q[c]);
             }
         });
     };
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(128) f4_eval_kernel(int mode, int64_t n, const
     f4_for_each<R, P, AW>(outer, BLOCK, tid, tc, ts, [&](int k, R phi) {
         if (mode == 0) { out[i * F + k] = (double)phi; return; }
 #pragma unroll
-        for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, W[(size_t)k * AW + c], q[c]);
+        for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, W[(size_t)k * AW + c], q[c]);
     });
     if (mode == 1) {
 #pragma unroll

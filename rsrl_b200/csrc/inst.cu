@@ -1,5 +1,6 @@
 // inst.cu — explicit kernel instantiations for one (dtype, domain) pair.
 // Compiled six times: -DRSRL_REAL=float|double -DRSRL_DOM=0|1|2 -DRSRL_SUFFIX=f32_d0 ...
+#include <cstring>
 #include "launch.h"
 
 namespace rsrl {
@@ -7,14 +8,23 @@ namespace rsrl {
 typedef RSRL_REAL R;
 constexpr int DOM = RSRL_DOM;
 
+// dynamic shared memory opt-in is a per-device attribute of the function: remember what each device was given
+static bool smem_configured(size_t* table, size_t smem, int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev & 63;
+    return smem <= table[dev & 63];
+}
+
 template <int BASIS, int P, int AW, int MODE, bool EXT>
 static cudaError_t launch_one(const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
     auto kern = fused_step_kernel<R, DOM, BASIS, P, AW, MODE, EXT>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};
+    int dev;
+    if (!smem_configured(configured, smem, &dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     kern<<<grid, block, smem, st>>>(a);
     return cudaGetLastError();
@@ -29,20 +39,52 @@ static cudaError_t launch_mode(int mode, bool ext, const StepArgs& a, int grid, 
 }
 
 template <int BASIS, int P, int AW, int MODE>
-static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
+static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem,
+                               cudaStream_t st, int* max_clusters) {
     auto kern = persistent_kernel<R, DOM, BASIS, P, AW, MODE>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};
+    static int coop_ok[64] = {0};  // 0 unknown, 1 cooperative + cluster launch accepted, -1 rejected by this driver
+    int dev;
+    if (!smem_configured(configured, smem, &dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
-    if (MODE != RSRL_PER_ENV && grid > 1) {
-        int per_sm = 0, dev = 0, sms = 0;
+    if (MODE != RSRL_PER_ENV && (grid > 1 || max_clusters)) {
+        // SHARED weights: the CTAs wait for each other every step, so the whole grid has to be co-resident.
+        const int cs = sy.cluster_size;
+        if (cs > 1) {
+            if (cs > 8) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (e != cudaSuccess) return e;
+            }
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeCooperative;
+            at[1].val.cooperative = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (max_clusters) return cudaOccupancyMaxActiveClusters(max_clusters, (const void*)kern, &cfg);
+            if (coop_ok[dev] >= 0) {
+                cfg.numAttrs = 2;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, k_steps, sy, pe);
+                if (e == cudaSuccess) { coop_ok[dev] = 1; return e; }
+                if (coop_ok[dev] == 1) return e;
+                cudaGetLastError();   // this driver does not combine the two attributes: co-residency was checked at create
+                coop_ok[dev] = -1;    // (cudaOccupancyMaxActiveClusters), launch as plain clusters
+                cfg.numAttrs = 1;
+            }
+            return cudaLaunchKernelEx(&cfg, kern, a, k_steps, sy, pe);
+        }
+        int per_sm = 0, sms = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem);
         if (e != cudaSuccess) return e;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (max_clusters) { *max_clusters = per_sm * sms; return cudaSuccess; }
         if ((long long)per_sm * sms < grid) return cudaErrorCooperativeLaunchTooLarge;
         void* args[] = {(void*)&a, (void*)&k_steps, (void*)&sy, (void*)&pe};
         return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st);
@@ -90,12 +132,12 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
 }
 
 cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy,
-                                                   const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st) {
+                                                   const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st, int* max_clusters) {
     constexpr int A = Domain<DOM>::A;
 #define RSRL_PERSIST(B, P, AWV)                                                                                   \
-    (mode == RSRL_SHARED ? persist_one<B, P, AWV, RSRL_SHARED>(a, k_steps, sy, pe, grid, block, smem, st)         \
-     : mode == RSRL_PER_ENV ? persist_one<B, P, AWV, RSRL_PER_ENV>(a, k_steps, sy, pe, grid, block, smem, st)     \
-                            : persist_one<B, P, AWV, kModeSharedTrace>(a, k_steps, sy, pe, grid, block, smem, st))
+    (mode == RSRL_SHARED ? persist_one<B, P, AWV, RSRL_SHARED>(a, k_steps, sy, pe, grid, block, smem, st, max_clusters)         \
+     : mode == RSRL_PER_ENV ? persist_one<B, P, AWV, RSRL_PER_ENV>(a, k_steps, sy, pe, grid, block, smem, st, max_clusters)     \
+                            : persist_one<B, P, AWV, kModeSharedTrace>(a, k_steps, sy, pe, grid, block, smem, st, max_clusters))
 #define X(B, P)                                   \
     if (k.basis == B && k.order == P) {           \
         if (k.aw == A) return RSRL_PERSIST(B, P, A); \

@@ -32,13 +32,14 @@ typedef cudaError_t (*fused_launch_fn)(const BasisKey&, int weight_mode, bool ex
                                        size_t smem, cudaStream_t);
 typedef cudaError_t (*eval_launch_fn)(const BasisKey&, const EvalArgs&, cudaStream_t);
 // persistent K-step kernel; SHARED mode is launched cooperatively (all CTAs co-resident)
+// max_clusters != nullptr: no launch, *max_clusters = co-resident clusters (CTAs when cluster_size == 1) of this shape
 typedef cudaError_t (*persist_launch_fn)(const BasisKey&, int weight_mode, const StepArgs&, int k_steps, const SyncArgs&,
-                                         const PeerArgs&, int grid, int block, size_t smem, cudaStream_t);
+                                         const PeerArgs&, int grid, int block, size_t smem, cudaStream_t, int* max_clusters);
 
 #define RSRL_DECL_INST(SUFFIX)                                                                                      \
     cudaError_t launch_fused_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t); \
     cudaError_t launch_eval_##SUFFIX(const BasisKey&, const EvalArgs&, cudaStream_t);                                 \
-    cudaError_t launch_persist_##SUFFIX(const BasisKey&, int, const StepArgs&, int, const SyncArgs&, const PeerArgs&, int, int, size_t, cudaStream_t);
+    cudaError_t launch_persist_##SUFFIX(const BasisKey&, int, const StepArgs&, int, const SyncArgs&, const PeerArgs&, int, int, size_t, cudaStream_t, int*);
 RSRL_DECL_INST(f32_d0) RSRL_DECL_INST(f32_d1) RSRL_DECL_INST(f32_d2)
 RSRL_DECL_INST(f64_d0) RSRL_DECL_INST(f64_d1) RSRL_DECL_INST(f64_d2)
 

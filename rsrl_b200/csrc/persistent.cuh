@@ -1,54 +1,56 @@
-// persistent.cuh — K batched steps in ONE launch (sm_100a): a persistent grid with one CTA per SM.
+// persistent.cuh — K batched steps in ONE launch (sm_100a): a persistent grid of thread-block clusters, one CTA per SM.
 //
 // Each CTA owns a contiguous slice of envs; with one env per thread the env state and the Fourier
 // tables of the current state live in registers for the whole launch (HBM traffic = one read + one
 // write of the state per launch).  SHARED weights need W_{t+1} = W_t + sum over ALL envs of the
 // step-t updates before anybody can take step t+1, so every step ends in a grid-wide, fixed-order
-// (bit-reproducible) reduction of F*A values.  A feature row k (its A values) is owned, in every
-// CTA, by one group of `lpr` adjacent lanes:
+// (bit-reproducible) reduction of NV = F*A values:
 //
-//   CTA    : env threads write phi(s_t) (feature-major rows, lane = env slot: conflict-free) while
-//            they evaluate Q(s_t), and their scaled TD error per action column.  A reducer thread owns
-//            4 rows x one slot segment (one load of the TD errors feeds 4 rows: the phase is bound by
-//            the number of LDS.128, ~5 cycles each), a shuffle butterfly over the segment lanes
-//            finishes the CTA partial.
-//   hop 1  : lane 0 publishes the row as a 16-byte LL line {3 payload words, epoch}.  In the leader
-//            of each group of ~sqrt(G) CTAs, lane m of row k spins on member m's (and m + lpr's)
-//            line; a butterfly sums the members.
-//   hop 2  : the leader's lane 0 publishes the group partial (parity double-buffered); in every CTA
-//            lane g of row k spins on group g's line, a butterfly sums the groups, lane 0 updates W.
-//   hop 3  : (multi-GPU) CTA 0 writes its rows into every rank's inbox through NVLink peer pointers,
-//            sums the ranks' rows in the same lane pattern and re-publishes the total locally.
+//   CTA     : env threads write phi(s_t) (feature-major rows, lane = env slot: conflict-free) while
+//             they evaluate Q(s_t), and their scaled TD error per action column.  A reducer thread owns
+//             4 rows x one slot segment (one load of the TD errors feeds 4 rows), a shuffle butterfly
+//             over the segment lanes finishes the CTA partial (`part`, NV values in shared memory).
+//   hop A   : (cluster, DSMEM) every member CTA copies its partial into the cluster leader's shared memory
+//             with ONE cp.async.bulk (shared::cta -> shared::cluster) that completes on the leader's mbarrier;
+//             the leader sums the partials in rank order.  No polling: the waiters sleep on the mbarrier.
+//   hop N   : (multi-GPU, NVLink) leader c of every GPU stores its cluster partial as 8-byte LL words
+//             {payload, epoch} into slot (rank, c) of EVERY GPU's inbox through cudaIpc-mapped peer pointers and
+//             sums the world's slot-c partials from its own inbox — all leaders of all GPUs in parallel.
+//   hop B   : (L2) the leaders exchange their (world-)cluster partials as 16-byte LL lines {3 payload words,
+//             epoch}; lane l of a row polls clusters l, l + lpr, ...; a butterfly gives the total.
+//   hop C   : (cluster, DSMEM) the leader copies the total into every member's shared memory (cp.async.bulk +
+//             the member's mbarrier); every CTA applies W += total to its own copy of W.
 //
-// No atomics, no fences, no grid.sync(), two barriers per step.  One LL hop costs ~700 cycles on a
-// B200 (tools/microbench/pingpong.cu); earlier versions and what they cost: profiles/r01_persistent_v1.md.
-// Launched with cudaLaunchCooperativeKernel so that all CTAs are co-resident (the spins need it).
+// Every CTA of every GPU performs the same additions in the same order, so all W copies stay bit-identical;
+// the order is restated on the host by oracle/oracle32.cpp (bit-exact parity of the fp32 path).
+// One DSMEM hop costs ~250 cycles, one L2 LL hop ~700 (tools/microbench/pingpong.cu); round 1's version
+// (two L2 hops polled by all 148 CTAs, NVLink hop serialised behind CTA 0) is in profiles/r01_final.md.
 #pragma once
 #include "kernels.cuh"
 
 namespace rsrl {
 
-constexpr int kMaxFan = 16;  // max CTAs per group and max groups (G <= 256)
 constexpr int kModeSharedTrace = 2;  // internal MODE: SHARED weights + per-env traces kept in shared memory
 constexpr int kMaxRanks = 8;
+constexpr int kMaxClusters = 64;     // leaders that exchange through L2
+constexpr int kMaxClusterSize = 16;
 
 struct SyncArgs {
-    uint4* stage1;  // [G][ROWS * LPW]              CTA partial rows
-    uint4* stage2;  // [2][n_groups][ROWS * LPW]    group partial rows (parity)
-    int group_size;
-    int n_groups;
+    uint4* stage;   // [2][n_clusters][ROWS * LPW]   (world-)cluster partial rows (parity double-buffered)
+    int cluster_size;
+    int n_clusters;
     int lpr;        // LL lanes per row (power of two <= 8, ROWS * lpr <= blockDim)
     int lpg;        // reducer lanes per group of 4 rows (power of two <= 32, ceil(ROWS / 4) * lpg <= blockDim)
     int seg_len;    // slots per reducer lane (odd multiple of the 16-byte vector width); row stride cap = lpg * seg_len
     int pe_smem;    // PER_ENV: keep every env's own W (F*A values, column `tid`) in shared memory for the whole launch
     int debug_skip; // development timing aid (RSRL_B200_DEBUG_SKIP): bit 0 skips the grid exchange, bit 1 the CTA reduce (wrong results)
+    uint32_t epoch_base;  // exchange epoch before the launch's first step (monotonic over the engine's life, never reset)
 };
 
 // Cross-GPU exchange (one process per GPU): every rank owns an inbox of 8-byte LL words
 // {payload, epoch} that its peers write through NVLink (cudaIpc-mapped pointers).
 struct PeerArgs {
-    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][ROWS * NDC * WPV] as seen from this GPU
-    uint4* stage3;            // [2][ROWS * LPW] local broadcast of the all-GPU total (parity)
+    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][n_clusters][NV * WPV] as seen from this GPU
     int rank, world;
 };
 
@@ -60,6 +62,10 @@ __device__ __forceinline__ uint2 ld_ll8_sys(const uint2* p) {
 __device__ __forceinline__ void st_ll8_sys(uint2* p, uint32_t payload, uint32_t epoch) {
     asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
 }
+// 16-byte LL line: data and flag travel in one aligned 16-byte access.  The PTX memory model only promises
+// single-copy atomicity per scalar element of a vector access; a B200 L2 serves an aligned 16-byte access as one
+// 32-byte-sector transaction (the property NCCL's LL128 protocol is built on).  tests/test_gpu_parity.py checks it:
+// every step of a full-size run against oracle32 bit for bit, and a 10^6-step run repeated with identical results.
 __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -68,6 +74,36 @@ __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
 __device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t c, uint32_t epoch) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(epoch) : "memory");
 }
+
+// ---- thread-block cluster / DSMEM primitives ----
+__device__ __forceinline__ uint32_t cl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cl_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {  // my shared::cta address -> the same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_expect_tx(uint32_t bar, uint32_t bytes) {  // one arrival + `bytes` pending transaction bytes
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_wait(uint32_t bar, uint32_t parity) {  // try_wait suspends the thread in hardware: not a busy poll
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra W_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+// bytes (multiple of 16) from my shared memory to the shared memory of another CTA of the cluster; completes on that CTA's mbarrier
+__device__ __forceinline__ void cl_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cl_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // A "row" carries NV <= 3 values.  fp32: one 16-byte LL line {v0, v1, v2, epoch}; fp64: one line per value.
 template <typename R, int NV> struct LLRow;
@@ -147,6 +183,9 @@ template <> struct Vec16<double> { typedef double2 type; static constexpr int N 
 __device__ __forceinline__ float vget(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 __device__ __forceinline__ double vget(const double2& v, int i) { return i == 0 ? v.x : v.y; }
 
+// NV values of R padded to a multiple of 16 bytes (bulk copies); host and device lay the shared memory out from this
+__host__ __device__ constexpr int persist_nvp(int nv, int rsz) { return (nv * rsz + 15) / 16 * 16 / rsz; }
+
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE>
 __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
     using Dom = Domain<DOM>;
@@ -160,6 +199,9 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     constexpr bool TRACE = MODE == kModeSharedTrace;        // eligibility traces resident in shared memory
     constexpr int ROWS = TRACE ? FA : F;                    // rows of the reduce buffer: z (F*A) or phi(s_t) (F)
     constexpr int NDC = TRACE ? 1 : AW;                     // values per row = rows of scaled TD errors
+    constexpr int NV = ROWS * NDC;                          // values of one dW partial (= F*A), index row * NDC + c == the flat F x A index
+    constexpr int NVP = persist_nvp(NV, (int)sizeof(R));
+    constexpr uint32_t NVB = NVP * sizeof(R);               // bytes of one partial (multiple of 16: bulk copies)
     constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
     constexpr int FApad = F * WS;
     using LR = LLRow<R, NDC>;
@@ -169,27 +211,46 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const int tid = threadIdx.x, BLOCK = blockDim.x, G = gridDim.x, b = blockIdx.x;
     const int64_t N = a.n;
     const int64_t per_cta = (N + G - 1) / G;
-    const int64_t base = (int64_t)b * per_cta;
+    const int64_t base = (int64_t)b * per_cta < N ? (int64_t)b * per_cta : N;
     const int64_t end = base + per_cta < N ? base + per_cta : N;
     const int n_chunks = (int)((per_cta + BLOCK - 1) / BLOCK);
     const bool resident = n_chunks == 1;  // one env per thread: state stays in registers across steps
     const int lpr = sy.lpr, lpg = sy.lpg, seg_len = sy.seg_len, cap = lpg * seg_len;
     constexpr int RPT = 4;                      // rows per reducer thread: one dcs load feeds RPT rows
     constexpr int ROWSP = (ROWS + RPT - 1) / RPT * RPT;
+    const int CS = SHAREDW ? sy.cluster_size : 1;
+    const int crank = CS > 1 ? (int)cl_ctarank() : 0;   // rank in the cluster; rank 0 leads
+    const int cid = b / CS;                             // cluster index
+    const bool leader = crank == 0;
 
-    // shared memory (SHARED mode).  Row stride cap = lpr * seg_len with seg_len / V::N odd: the lpr lanes
-    // of a row read 16-byte groups seg * seg_len + slot that fall into distinct bank groups.  Slots
+    // shared memory (SHARED modes).  Row stride cap = lpg * seg_len with seg_len / V::N odd: the lpg lanes
+    // of a row group read 16-byte groups seg * seg_len + slot that fall into distinct bank groups.  Slots
     // >= BLOCK are zero and stay zero.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* Wsm = reinterpret_cast<R*>(smem_raw);  // [FApad]
+    unsigned long long* mbars = reinterpret_cast<unsigned long long*>(smem_raw);  // [0] leader: members' partials, [1] member: the total
+    R* part = reinterpret_cast<R*>(smem_raw + 16);  // [NVP]     this CTA's dW partial (bulk-copy source)
+    R* totbuf = part + NVP;                         // [NVP]     grid total (leader: bulk-copy source, member: destination)
+    R* inbuf = totbuf + NVP;                        // [CS][NVP] leader: the members' partials; slot 0: the grid total (bulk-copy source)
+    R* Wsm = inbuf + (size_t)CS * NVP;        // [FApad]
     R* red = Wsm + FApad;                     // [ROWSP][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
     R* dcs = red + (size_t)ROWSP * cap;       // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
-    R* part = dcs + (size_t)NDC * cap;        // [ROWSP][NDC] this CTA's dW rows (reducers -> LL lanes)
+    const uint32_t mb_in = cl_smem_u32(&mbars[0]), mb_tot = cl_smem_u32(&mbars[1]);
 
     if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
         for (int j = tid; j < (ROWSP + NDC) * cap; j += BLOCK) red[j] = (R)0;
-        __syncthreads();
+        for (int j = tid; j < NVP; j += BLOCK) { part[j] = (R)0; totbuf[j] = (R)0; }
+        if (CS > 1) {
+            if (tid == 0) {
+                cl_mbar_init(mb_in, 1);
+                cl_mbar_init(mb_tot, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            cl_sync();  // every CTA's barriers are initialised before anybody sends
+        } else {
+            __syncthreads();
+        }
     }
     const R* Wg = static_cast<const R*>(a.W);
     R* Wpe = reinterpret_cast<R*>(smem_raw);  // PER_ENV + pe_smem: [FA][BLOCK], column tid = this env's weights
@@ -219,12 +280,10 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const int rg = tid / lpg, rseg = tid % lpg;
     const bool reducer = SHAREDW && rg < ROWSP / RPT;
     const bool warp_red = SHAREDW && (tid & ~31) < (ROWSP / RPT) * lpg;  // warp-uniform
-    // LL row ownership: lanes [row * lpr, (row + 1) * lpr) own row `row` in the grid exchange
+    // LL row ownership: lanes [row * lpr, (row + 1) * lpr) own row `row` in the exchanges between leaders
     const int row = tid / lpr, rl = tid % lpr;
     const bool row_valid = SHAREDW && row < ROWS;
     const bool warp_rows = SHAREDW && (tid & ~31) < ROWS * lpr;  // warp-uniform: this warp owns at least one row
-    const int grp = b / sy.group_size;
-    const bool leader = b % sy.group_size == 0;
 
     const bool prof = a.phase_prof != nullptr && tid == 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0;
@@ -280,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         R w[AW];
                         wrow(k, w);
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, w[c], q[c]);
+                        for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, w[c], q[c]);
                     });
                 };
                 auto evalN = [&](const typename GB::Tab& tab, R* q) {
@@ -290,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         R w[AW];
                         wrow(k, w);
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) q[c] = O::fma(phi, w[c], q[c]);
+                        for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, w[c], q[c]);
                     });
                 };
                 auto prep = [](const double* st, typename GB::Tab& tb) { grid_prepare<R, Dom, P, BASIS>(st, tb); };
@@ -373,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         }
 
         if (SHAREDW) {
-            // CTA partial: butterfly over the lpg lanes of each row group, lane 0 hands the rows to the LL lanes
+            // CTA partial: butterfly over the lpg lanes of each row group, lane 0 writes the rows to `part`
             if (warp_red) {
                 for (int off = 1; off < lpg; off <<= 1) {
 #pragma unroll
@@ -385,90 +444,113 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
                     for (int r = 0; r < RPT; ++r)
 #pragma unroll
-                        for (int c = 0; c < NDC; ++c) part[(rg * RPT + r) * NDC + c] = racc[r][c];
+                        for (int c = 0; c < NDC; ++c)
+                            if (rg * RPT + r < ROWS) part[(rg * RPT + r) * NDC + c] = racc[r][c];
                 }
             }
             __syncthreads();
-            if (warp_rows) {
-                const uint32_t epoch = (uint32_t)(t + 1);
-                const int par = (int)(t & 1);
-                R dW[NDC];
-#pragma unroll
-                for (int c = 0; c < NDC; ++c) dW[c] = row_valid ? part[row * NDC + c] : (R)0;
-                if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
-                if (G > 1 && !(sy.debug_skip & 1)) {
-                    const size_t rstride = (size_t)ROWS * LPW;  // lines between two producers
-                    if (row_valid && rl == 0) LR::publish(sy.stage1 + (size_t)b * rstride + (size_t)row * LPW, dW, epoch);
-                    if (leader) {  // hop 1: lane m gathers member m (and m + lpr, ...) of this row
-                        const int first = grp * sy.group_size;
-                        const int cnt = G - first < sy.group_size ? G - first : sy.group_size;
-                        R gsum[NDC];
-                        ll_gather<R, NDC>(sy.stage1 + (size_t)first * rstride + (size_t)row * LPW, rstride, rl, lpr, cnt, epoch, row_valid, gsum);
-                        __syncwarp();
-                        row_butterfly<R, NDC>(gsum, lpr);
-                        if (row_valid && rl == 0) LR::publish(sy.stage2 + ((size_t)par * sy.n_groups + grp) * rstride + (size_t)row * LPW, gsum, epoch);
+            if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
+            const uint32_t epoch = sy.epoch_base + (uint32_t)step + 1u;
+            const int par = (int)(epoch & 1u);
+            const uint32_t ph = (uint32_t)(step & 1);  // one mbarrier completion per step
+            const R* total = part;                     // one CTA (or exchange skipped): its partial is the total
+            if ((G > 1 || pe.world > 1) && !(sy.debug_skip & 1)) {
+                if (!leader) {
+                    // hop A (send): my partial -> the leader's inbuf[crank]; then sleep until the total arrives (hop C)
+                    if (tid == 0) {
+                        cl_mbar_expect_tx(mb_tot, NVB);
+                        cl_fence_async();
+                        cl_bulk_copy(cl_mapa(cl_smem_u32(inbuf + (size_t)crank * NVP), 0), cl_smem_u32(part), NVB, cl_mapa(mb_in, 0));
                     }
-                    // hop 2: lane g gathers group g (and g + lpr, ...) of this row
-                    ll_gather<R, NDC>(sy.stage2 + (size_t)par * sy.n_groups * rstride + (size_t)row * LPW, rstride, rl, lpr, sy.n_groups, epoch, row_valid, dW);
-                    __syncwarp();
-                    row_butterfly<R, NDC>(dW, lpr);
-                }
-                if (pe.world > 1) {
-                    // hop 3 (NVLink): CTA 0 of every GPU writes its rows into every rank's inbox, gathers the world's
-                    // rows from its own inbox (lane r <-> rank r, butterfly => the same rank-pairing order on every
-                    // GPU => bit-identical replicas) and re-publishes the total for the local CTAs.
-                    constexpr int RW = NDC * WPV;  // 32-bit payload words per row
-                    if (b == 0) {
-                        if (row_valid && rl == 0) {
-                            uint32_t w[RW];
+                    cl_mbar_wait(mb_tot, ph);
+                } else {
+                    // hop A (receive): cluster partial = the members' partials summed in rank order
+                    if (CS > 1) {
+                        if (tid == 0) cl_mbar_expect_tx(mb_in, (uint32_t)(CS - 1) * NVB);
+                        cl_mbar_wait(mb_in, ph);
+                    }
+                    for (int j = tid; j < NV; j += BLOCK) {
+                        R acc = part[j];
+                        for (int r = 1; r < CS; ++r) acc += inbuf[(size_t)r * NVP + j];
+                        totbuf[j] = acc;
+                    }
+                    const int NCL = sy.n_clusters;
+                    if (NCL > 1 || pe.world > 1) {
+                        __syncthreads();  // (leader CTAs only; the branch is CTA-uniform) cluster partial complete in totbuf
+                        R dW[NDC];
+                        if (warp_rows) {
 #pragma unroll
-                            for (int c = 0; c < NDC; ++c) {
-                                if (WPV == 1) w[c] = __float_as_uint((float)dW[c]);
-                                else { const unsigned long long u = (unsigned long long)__double_as_longlong((double)dW[c]); w[c * WPV] = (uint32_t)u; w[c * WPV + WPV - 1] = (uint32_t)(u >> 32); }
+                            for (int c = 0; c < NDC; ++c) dW[c] = row_valid ? totbuf[row * NDC + c] : (R)0;
+                            if (pe.world > 1) {
+                                // hop N (NVLink): slot (my rank, cid) of every GPU's inbox <- my cluster partial; then sum the world's
+                                // slot-cid partials: lane l <-> ranks l, l + lpr, ...; butterfly => the same order on every GPU
+                                constexpr int RW = NDC * WPV;  // 32-bit payload words per row
+                                if (row_valid && rl == 0) {
+                                    uint32_t w[RW];
+#pragma unroll
+                                    for (int c = 0; c < NDC; ++c) {
+                                        if (WPV == 1) w[c] = __float_as_uint((float)dW[c]);
+                                        else { const unsigned long long u = (unsigned long long)__double_as_longlong((double)dW[c]); w[c * WPV] = (uint32_t)u; w[c * WPV + WPV - 1] = (uint32_t)(u >> 32); }
+                                    }
+                                    for (int r = 0; r < pe.world; ++r) {
+                                        uint2* dst = pe.inbox[r] + ((((size_t)par * pe.world + pe.rank) * NCL + cid) * ROWS + row) * RW;
+#pragma unroll
+                                        for (int q = 0; q < RW; ++q) st_ll8_sys(dst + q, w[q], epoch);
+                                    }
+                                }
+                                R tot[NDC];
+#pragma unroll
+                                for (int c = 0; c < NDC; ++c) tot[c] = (R)0;
+                                if (row_valid) {
+                                    for (int r = rl; r < pe.world; r += lpr) {
+                                        const uint2* src = pe.inbox[pe.rank] + ((((size_t)par * pe.world + r) * NCL + cid) * ROWS + row) * RW;
+                                        uint32_t w[RW];
+#pragma unroll
+                                        for (int q = 0; q < RW; ++q) {
+                                            uint2 v = ld_ll8_sys(src + q);
+                                            while (v.y != epoch) v = ld_ll8_sys(src + q);
+                                            w[q] = v.x;
+                                        }
+#pragma unroll
+                                        for (int c = 0; c < NDC; ++c) {
+                                            if (WPV == 1) tot[c] += (R)__uint_as_float(w[c]);
+                                            else tot[c] += (R)__longlong_as_double((long long)(((unsigned long long)w[c * WPV + WPV - 1] << 32) | w[c * WPV]));
+                                        }
+                                    }
+                                }
+                                __syncwarp();
+                                row_butterfly<R, NDC>(tot, lpr);
+#pragma unroll
+                                for (int c = 0; c < NDC; ++c) dW[c] = tot[c];
                             }
-                            for (int r = 0; r < pe.world; ++r) {
-                                uint2* dst = pe.inbox[r] + (((size_t)par * pe.world + pe.rank) * ROWS + row) * RW;
+                            if (NCL > 1) {
+                                // hop B (L2): publish my (world-)cluster partial, gather every cluster's: lane l <-> clusters l, l + lpr, ...
+                                const size_t rstride = (size_t)ROWS * LPW;  // lines between two producers
+                                uint4* st = sy.stage + (size_t)par * NCL * rstride;
+                                if (row_valid && rl == 0) LR::publish(st + (size_t)cid * rstride + (size_t)row * LPW, dW, epoch);
+                                ll_gather<R, NDC>(st + (size_t)row * LPW, rstride, rl, lpr, NCL, epoch, row_valid, dW);
+                                __syncwarp();
+                                row_butterfly<R, NDC>(dW, lpr);
+                            }
+                            if (row_valid && rl == 0) {  // slot 0 of inbuf (no member writes it) takes the total
 #pragma unroll
-                                for (int q = 0; q < RW; ++q) st_ll8_sys(dst + q, w[q], epoch);
+                                for (int c = 0; c < NDC; ++c) inbuf[row * NDC + c] = dW[c];
                             }
                         }
-                        R tot[NDC];
-#pragma unroll
-                        for (int c = 0; c < NDC; ++c) tot[c] = (R)0;
-                        if (row_valid) {
-                            for (int r = rl; r < pe.world; r += lpr) {
-                                const uint2* src = pe.inbox[pe.rank] + (((size_t)par * pe.world + r) * ROWS + row) * RW;
-                                uint32_t w[RW];
-#pragma unroll
-                                for (int q = 0; q < RW; ++q) {
-                                    uint2 v = ld_ll8_sys(src + q);
-                                    while (v.y != epoch) v = ld_ll8_sys(src + q);
-                                    w[q] = v.x;
-                                }
-#pragma unroll
-                                for (int c = 0; c < NDC; ++c) {
-                                    if (WPV == 1) tot[c] += (R)__uint_as_float(w[c]);
-                                    else tot[c] += (R)__longlong_as_double((long long)(((unsigned long long)w[c * WPV + WPV - 1] << 32) | w[c * WPV]));
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        row_butterfly<R, NDC>(tot, lpr);
-#pragma unroll
-                        for (int c = 0; c < NDC; ++c) dW[c] = tot[c];
-                        if (G > 1 && row_valid && rl == 0) LR::publish(pe.stage3 + ((size_t)par * ROWS + row) * LPW, dW, epoch);
+                        total = inbuf;
                     } else {
-                        ll_gather<R, NDC>(pe.stage3 + ((size_t)par * ROWS + row) * LPW, 0, 0, 1, (row_valid && rl == 0) ? 1 : 0, epoch, row_valid, dW);
+                        total = totbuf;  // one cluster, one GPU: the cluster partial is the total
+                    }
+                    __syncthreads();  // total complete
+                    // hop C: the total -> every member's totbuf
+                    if (tid >= 1 && tid < CS) {
+                        cl_fence_async();
+                        cl_bulk_copy(cl_mapa(cl_smem_u32(totbuf), (uint32_t)tid), cl_smem_u32(total), NVB, cl_mapa(mb_tot, (uint32_t)tid));
                     }
                 }
-                if (row_valid && rl == 0) {
-#pragma unroll
-                    for (int c = 0; c < NDC; ++c) {
-                        const int idx = TRACE ? row : row * AW + c;  // flat F x A index
-                        Wsm[(idx / AW) * WS + idx % AW] += dW[c];
-                    }
-                }
+                if (!leader) total = totbuf;
             }
+            for (int j = tid; j < NV; j += BLOCK) Wsm[(j / AW) * WS + j % AW] += total[j];
             if (prof) { c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
             __syncthreads();
             if (prof) { c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
@@ -496,6 +578,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     if (SHAREDW && b == 0) {
         for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[(j / AW) * WS + j % AW];
     }
+    if (SHAREDW && CS > 1) cl_sync();  // nobody leaves while a bulk copy may still read or write its shared memory
 }
 
 }  // namespace rsrl

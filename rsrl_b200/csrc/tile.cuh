@@ -17,9 +17,8 @@ struct TileArgs {
     TileParams tp;
     int dense;                    // 1: tile_dense_kernel (per-CTA shared-memory accumulation + dense reduce-scatter), 0: RED atomics
     unsigned long long* G;        // RED path: [4][M * AW] fixed-point dW accumulators; dense path: [grid + 1][M * AW] partials + totals
-    unsigned long long* barrier;  // monotonically increasing arrival counter
-    unsigned long long barrier_base;  // batched steps (fused or handle) completed before this launch: barrier target
-                                      // and rotation index of the dW tables
+    unsigned long long* barrier;  // arrival counter, zeroed by the host before every launch
+    unsigned long long barrier_base;  // batched steps (fused or handle) completed before this launch: rotation index of the dW tables
     double fx_scale;              // 2^40 (f32) / 2^44 (f64)
 };
 
@@ -105,7 +104,7 @@ __global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs 
                 }
             }
         }
-        if (G > 1) grid_barrier(ta.barrier, (ta.barrier_base + (unsigned long long)step + 1ull) * (unsigned long long)G);
+        if (G > 1) grid_barrier(ta.barrier, ((unsigned long long)step + 1ull) * (unsigned long long)G);  // launch-local target: the host zeroes the counter before every launch (launches may differ in grid size)
         else { __threadfence(); __syncthreads(); }
         // every CTA applies the same dW to its W copy; the table for step t+2 is cleared cooperatively
         unsigned long long* Gz = ta.G + (size_t)((rot + 2) & 3) * MA;

@@ -16,8 +16,10 @@ static cudaError_t tile_one(const StepArgs& a, int k_steps, const TileArgs& ta, 
               : ta.tp.n_tilings <= 8
                     ? (block > 768 ? tile_dense_kernel<R, DOM, AW, EXT, 1024, 8> : block > 512 ? tile_dense_kernel<R, DOM, AW, EXT, 768, 8> : tile_dense_kernel<R, DOM, AW, EXT, 512, 8>)
                     : (block > 768 ? tile_dense_kernel<R, DOM, AW, EXT, 1024> : block > 512 ? tile_dense_kernel<R, DOM, AW, EXT, 768> : tile_dense_kernel<R, DOM, AW, EXT, 512>);
-    static size_t configured_v[7] = {0, 0, 0, 0, 0, 0, 0};
-    size_t& configured = configured_v[!ta.dense ? 0 : (block > 768 ? 3 : block > 512 ? 2 : 1) + (ta.tp.n_tilings <= 8 ? 3 : 0)];
+    static size_t configured_v[64][7] = {{0}};  // per device (the opt-in is a per-device attribute) and kernel variant
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_v[dev & 63][!ta.dense ? 0 : (block > 768 ? 3 : block > 512 ? 2 : 1) + (ta.tp.n_tilings <= 8 ? 3 : 0)];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

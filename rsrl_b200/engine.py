@@ -124,6 +124,14 @@ class Engine:
         check(self.lib.rsrl_engine_get_env_stats(self.h, ip(n_ep), ip(last), u64p(h)))
         return n_ep, last, h
 
+    def launch_shape(self):
+        """rsrl_engine_get_launch_shape as a dict (the fp32 summation order is a function of it: oracle/oracle32.cpp)."""
+        out = np.zeros(16, dtype=np.int32)
+        check(self.lib.rsrl_engine_get_launch_shape(self.h, ip(out)))
+        keys = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "lpg", "seg_len", "pe_smem", "world",
+                "rank", "peers", "smem", "tile", "f4"]
+        return dict(zip(keys, (int(v) for v in out)))
+
     def set_epsilon(self, eps):
         check(self.lib.rsrl_engine_set_epsilon(self.h, eps))
 
@@ -264,4 +272,12 @@ def trace_update(rule, gamma, lam, alpha, z, grad):
 def philox(seed, draw, stream, env_offset, n):
     out = np.empty((n, 4), dtype=np.uint32)
     check(abi.load().rsrl_philox(seed, draw, stream, env_offset, n, u32p(out)))
+    return out
+
+
+def math_probe(fn, x):
+    """fn: 0 cos64, 1 sin64, 2 sinpi32, 3 cospi32, 4 exp32 — evaluated on the GPU (csrc/device.cuh "rsrl math")."""
+    x = _f64(x).ravel()
+    out = np.empty_like(x)
+    check(abi.load().rsrl_math_probe(fn, x.size, dp(x), dp(out)))
     return out

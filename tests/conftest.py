@@ -22,6 +22,15 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def oracle32():
+    """oracle32: the fp32 device arithmetic compiled for the host (test infrastructure; oracle/oracle32.cpp)."""
+    from oracle import pyoracle32
+    pyoracle32.build()
+    pyoracle32.lib()
+    return pyoracle32
+
+
+@pytest.fixture(scope="session")
 def rsrl():
     """The product: ctypes view of librsrl_b200.so through the C ABI.  No fallback."""
     import rsrl_b200

@@ -522,6 +522,33 @@ def test_tile_engine_variants_f64(E, oracle, kw, monkeypatch):
                 _compare_engines(e, o, w_tol=1e-9, s_tol=1e-9)
 
 
+def test_tile_red_kernel_handle_then_step(E, oracle, monkeypatch):
+    """RED-atomics TileCoding kernel: handle(n < N) launches fewer CTAs than step(); the grid barrier targets are
+    launch-local, so mixing the two neither hangs nor lets a CTA read the table early (either order)."""
+    monkeypatch.setenv("RSRL_B200_TILE_DENSE", "0")
+    cfg = _tile_cfg(n_envs=3000)
+    rng = np.random.default_rng(8)
+    lo, hi = oracle.domain_limits(CP)
+    s = rng.uniform(lo, hi, size=(300, 4)) * 0.5
+    a = rng.integers(0, 2, 300).astype(np.int32)
+    ns, r, term = oracle.domain_step(CP, s, a)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        for _ in range(2):
+            e.handle(s, a, r, ns, term, draw_idx=1)
+            o.handle(s, a, r, ns, term, draw_idx=1)
+            e.step(3)
+            o.step(3)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9, s_tol=1e-9)
+        e.handle(s[:100], a[:100], r[:100], ns[:100], term[:100], draw_idx=2)   # a single CTA: no barrier at all
+        o.handle(s[:100], a[:100], r[:100], ns[:100], term[:100], draw_idx=2)
+        e.step(2)
+        o.step(2)
+        e.sync()
+        _compare_engines(e, o, w_tol=1e-9, s_tol=1e-9)
+
+
 def test_tile_handle_and_policy_entry_points(E, oracle):
     cfg = _tile_cfg(n_envs=200)
     rng = np.random.default_rng(3)
@@ -837,6 +864,12 @@ def test_error_behaviour(E):
     with pytest.raises(abi.RsrlError) as ei:
         E.Engine(_mc_cfg(n_envs=0))
     assert ei.value.code == abi.EINVAL
+    # raw int32 / double config fields: a typo must not silently change the learning semantics
+    for bad in (dict(trace_rule=3), dict(update_scale=2), dict(init_mode=2), dict(gamma=float("nan")), dict(lr=float("inf")),
+                dict(n_envs=8, env_offset=4, n_envs_global=8)):
+        with pytest.raises(abi.RsrlError) as ei:
+            E.Engine(_mc_cfg(**{**dict(n_envs=8), **bad}))
+        assert ei.value.code == abi.EINVAL, bad
     with pytest.raises(abi.RsrlError) as ei:   # per-env weights: transition i belongs to agent i
         with E.Engine(_mc_cfg(n_envs=8, weight_mode=abi.PER_ENV)) as e2:
             e2.handle(np.zeros((3, 2)), np.zeros(3, dtype=np.int32), np.zeros(3), np.zeros((3, 2)), np.zeros(3, dtype=np.uint8))
