@@ -64,7 +64,14 @@ typedef enum rsrl_basis { RSRL_FOURIER = 0, RSRL_POLYNOMIAL = 1, RSRL_TILE_CODIN
 typedef enum rsrl_algo {
     RSRL_QLEARNING = 0, RSRL_SARSA = 1, RSRL_EXPECTED_SARSA = 2,
     RSRL_SARSA_LAMBDA = 3, RSRL_Q_LAMBDA = 4, RSRL_TD_LAMBDA = 5, RSRL_TD0 = 6,
-    RSRL_PAL = 7 /* persistent advantage learning, control/td/pal.rs:35-59 (update error = alpha * residual) */
+    RSRL_PAL = 7, /* persistent advantage learning, control/td/pal.rs:35-59 (update error = alpha * residual) */
+    /* Two weight tables (rsrl_engine_{get,set}_aux_weights reaches the second one):
+     * GreedyGQ (control/td/greedy_gq.rs:73-141; examples/greedy_gq.rs): fa_q = the weights (SGD `lr`), fa_td = the aux weights
+     *   (SGD `alpha`); three updates per transition: fa_q(s, a) += td_error, fa_q(s', argmax Q(s')) += -gamma * td_est, fa_td(s, a) += td_error - td_est.
+     * A2C (examples/a2c.rs:24-66 = control/ac.rs:100-114 + policies/softmax.rs:113-129,146-160 with a SARSA critic): the critic's Q = the
+     *   weights (SGD `lr`), the Gibbs policy's own LFA = the aux weights; actions are sampled from softmax(theta^T phi(s) / tau) (tau in
+     *   `epsilon`, policy must be RSRL_SOFTMAX); advantage = Q(s)[a] - sum_i Q(s)_i pi_i after the critic update; theta += (alpha * advantage) * grad_log pi(a | s). */
+    RSRL_GREEDY_GQ = 8, RSRL_A2C = 9
 } rsrl_algo_t;
 /* rsrl/src/policies/{greedy,epsilon_greedy,random,softmax}.rs.  RSRL_SOFTMAX (= Gibbs, softmax.rs:38): probabilities
  * softmax_stable(Q(s), tau) (softmax.rs:15-36), sample by inverse CDF (policies/mod.rs:46-61), mode = argmax_first of the
@@ -153,6 +160,9 @@ int rsrl_engine_get_episode_steps(rsrl_engine_t* e, int32_t* out /* N */);
 /* Parameterised::weights() — F x A (SHARED) or N x F x A (PER_ENV), f64 row-major */
 int rsrl_engine_get_weights(rsrl_engine_t* e, double* out);
 int rsrl_engine_set_weights(rsrl_engine_t* e, const double* in);
+/* second weight table of the two-table agents (GreedyGQ: fa_td, A2C: the policy's LFA), same shape as the weights */
+int rsrl_engine_get_aux_weights(rsrl_engine_t* e, double* out);
+int rsrl_engine_set_aux_weights(rsrl_engine_t* e, const double* in);
 /* Trace::buffer (traces.rs:6-12) — N x F x A (Q traces) or N x F (TD(lambda)) */
 int rsrl_engine_get_traces(rsrl_engine_t* e, double* out);
 int rsrl_engine_set_traces(rsrl_engine_t* e, const double* in);
@@ -176,12 +186,28 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
                        const double* rewards, const double* to_states, const uint8_t* terminal,
                        uint64_t draw, double* td_out);
 
+/* ---- Domain::rollout / Trajectory (rsrl_domains/src/lib.rs:334-409,448-479) ----
+ * n independent rollouts with the engine's CURRENT weights held fixed (no learning): env i starts from init_states[i] (NULL: the
+ * config's start distribution, draw index `draw`) and follows pi = Policy::mode (greedy != 0: greedy.rs:83 find_max / softmax.rs:141;
+ * A2C: the policy table) or Policy::sample with RNG draw (draw + step) until a terminal observation or until step_limit - 1 steps
+ * are recorded (lib.rs:472-476: `iter.take(sl.saturating_sub(1))`; step_limit <= 0: T_max steps).  Layout = Trajectory{start, steps}:
+ *   start_out    n x D          Trajectory::start (state of the first observation)
+ *   next_out     n x T_max x D  steps[j].0 (state of the observation after step j)
+ *   actions_out  n x T_max      steps[j].1        rewards_out n x T_max  steps[j].2
+ *   terminal_out n x T_max      1 where steps[j].0 is Observation::Terminal
+ *   len_out      n              Trajectory::n_transitions(); entries j >= len are untouched
+ * T_max = max(step_limit - 1, 1) is the caller's row length (the first step is always taken, lib.rs:460-462). */
+int rsrl_engine_rollout(rsrl_engine_t* e, int64_t n, const double* init_states, int64_t step_limit, int32_t greedy, uint64_t draw,
+                        double* start_out, double* next_out, int32_t* actions_out, double* rewards_out, uint8_t* terminal_out,
+                        int32_t* len_out);
+
 /* ---- introspection for the parity tests ---- */
 /* Launch shape of the fused loop: out = {persistent kernel in use, its mode, CTAs, cluster size, clusters, threads per CTA,
  * LL lanes per row, reducer lanes per row group, slots per reducer lane, PER_ENV weights in shared memory, world, rank,
- * peers attached, dynamic shared memory bytes, TileCoding engine, large-basis engine (1 + tensor-core bits)}.
+ * peers attached, dynamic shared memory bytes, TileCoding engine, large-basis engine (1 + tensor-core bits),
+ * counting (fixed-point) exchange in use, 0...}.
  * The order of the fp32 dW sums is a function of these numbers; oracle/oracle32.cpp replays it on the host. */
-int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[16]);
+int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[24]);
 /* The elementary functions of the device arithmetic (csrc/device.cuh "rsrl math") evaluated on the GPU:
  * fn 0 cos (f64), 1 sin (f64), 2 sin(pi x) (fp32), 3 cos(pi x) (fp32), 4 exp (fp32). */
 int rsrl_math_probe(int32_t fn, int64_t n, const double* x, double* out);

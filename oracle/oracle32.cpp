@@ -9,8 +9,8 @@
  *     --fmad=false), in which every rounding is explicit and the elementary functions are the project's own
  *     (device.cuh "rsrl math"), not libm / the CUDA math library;
  *   - the ORDER of the fp32 sums of the SHARED-weights update is replayed from persistent.cuh: slot segments summed
- *     sequentially by the reducer lanes, butterfly over the lanes, cluster members in rank order, ranks and clusters
- *     lane-strided + butterfly.  That order is a function of the launch shape (rsrl_engine_get_launch_shape), which the
+ *     sequentially by the reducer lanes, butterfly over the lanes; then either the counting exchange (CTA partials on the
+ *     2^-40 fixed-point grid, integer sums) or cluster members in rank order, ranks and clusters lane-strided + butterfly.  That order is a function of the launch shape (rsrl_engine_get_launch_shape), which the
  *     caller passes in.
  * What this pins: actions, episode step counts and length hashes, states, TD errors, weights and traces of a free-running
  * fp32 engine — exactly (tests/test_gpu_parity.py: test_f32_*_bit_exact_vs_oracle32).  How far fp32 is from the
@@ -35,7 +35,14 @@ constexpr int kModeTrace = 2;  // persistent.cuh kModeSharedTrace
 
 struct Shape {
     int persistent, mode, grid, cs, ncl, block, lpr, lpg, seg_len, pe_smem;
+    int fx;  // counting (fixed-point) exchange instead of the cluster + LL-line exchange
 };
+
+// persistent.cuh: fx_from_float / fx_to_float / kFxScale / kFxLimit (that header needs nvcc; the three lines are restated here)
+constexpr double kFxScale = 1099511627776.0;  // 2^40
+constexpr float kFxLimit = 16384.0f;
+long long fx_from_float(float x) { return (long long)llrint((double)x * kFxScale); }
+float fx_to_float(long long q) { return (float)((double)q * (1.0 / kFxScale)); }
 
 struct RankState {
     std::vector<double> states;
@@ -272,6 +279,18 @@ void engine_step(Engine& e, int64_t k_steps) {
             std::vector<float> total_dw(FA);
             if (G == 1 && e.world == 1) {
                 for (int j = 0; j < FA; ++j) total_dw[j] = parts[j];
+            } else if (sh.fx) {
+                // counting exchange: every CTA partial goes to the 2^-40 grid (one rounding), integer sums over CTAs and ranks
+                // (order independent), one rounding back to fp32
+                for (int j = 0; j < FA; ++j) {
+                    long long acc = 0;
+                    for (int w = 0; w < e.world * G; ++w) {
+                        float x = parts[(size_t)w * FA + j];
+                        if (!(fabsf(x) < kFxLimit)) { e.ranks[w / G].nonfinite = 1; x = 0.0f; }
+                        acc += fx_from_float(x);
+                    }
+                    total_dw[j] = fx_to_float(acc);
+                }
             } else {
                 // hop A: cluster partial = members in rank order
                 std::vector<float> cp((size_t)e.world * NCL * FA);
@@ -348,7 +367,7 @@ o32_engine_t* o32_engine_create(const rsrl_config_t* cfg, const int32_t* shape, 
     if (!cfg || !shape || world < 1 || cfg->dtype != RSRL_F32 || cfg->basis == RSRL_TILE_CODING || !shape[0]) return nullptr;
     Engine* e = new Engine();
     e->cfg = *cfg;
-    e->sh = Shape{shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6], shape[7], shape[8], shape[9]};
+    e->sh = Shape{shape[0], shape[1], shape[2], shape[3], shape[4], shape[5], shape[6], shape[7], shape[8], shape[9], shape[16]};
     e->world = world;
     e->threads = threads > 0 ? threads : 1;
     e->D = dom_dim(cfg->domain); e->A = dom_actions(cfg->domain); e->AW = td_pred(cfg->algo) ? 1 : e->A;

@@ -72,7 +72,7 @@ def _i(a):
 SHAPE_KEYS = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "lpg", "seg_len", "pe_smem"]
 
 
-def host_shape(cfg, grid=None, cluster_size=8, block=None):
+def host_shape(cfg, grid=None, cluster_size=1, block=None, fx=1):
     """A launch shape computed like rsrl_b200/csrc/abi.cu:persistent_shape, for tests that have no GPU to ask
     (rsrl_engine_get_launch_shape is authoritative on a GPU box)."""
     D = 2 if cfg.domain == _abi.MOUNTAIN_CAR else 4
@@ -83,12 +83,12 @@ def host_shape(cfg, grid=None, cluster_size=8, block=None):
     N = cfg.n_envs
     if cfg.weight_mode == _abi.PER_ENV:
         return dict(persistent=1, mode=_abi.PER_ENV, grid=(N + 127) // 128, cluster_size=1, n_clusters=1, block=128, lpr=1, lpg=1,
-                    seg_len=4, pe_smem=1)
+                    seg_len=4, pe_smem=1, fx=0)
     rows = F * aw if trace else F
     if grid is None:
         g0 = min((N + 127) // 128, 148)
         cs = 1 if g0 == 1 else cluster_size
-        grid = min((g0 + cs - 1) // cs * cs, 128 if cs > 1 else 148)
+        grid = min((g0 + cs - 1) // cs * cs, 132 if cs > 1 else 148)
     else:
         cs = 1 if grid == 1 else cluster_size
     per_cta = (N + grid - 1) // grid
@@ -107,7 +107,7 @@ def host_shape(cfg, grid=None, cluster_size=8, block=None):
     if (seg_len // vn) % 2 == 0:
         seg_len += vn
     return dict(persistent=1, mode=2 if trace else _abi.SHARED, grid=grid, cluster_size=cs, n_clusters=grid // cs, block=block,
-                lpr=lpr, lpg=lpg, seg_len=seg_len, pe_smem=0)
+                lpr=lpr, lpg=lpg, seg_len=seg_len, pe_smem=0, fx=fx if cs == 1 else 0)
 
 
 class Engine:
@@ -115,9 +115,10 @@ class Engine:
 
     def __init__(self, cfg, shape, world=1, threads=None):
         self.cfg, self.world = cfg, world
-        sh = np.zeros(16, dtype=np.int32)
+        sh = np.zeros(24, dtype=np.int32)
         for k, key in enumerate(SHAPE_KEYS):
             sh[k] = shape[key]
+        sh[16] = shape.get("fx", 0)
         self.shape = dict(shape)
         self.D = 2 if cfg.domain == _abi.MOUNTAIN_CAR else 4
         self.A = 2 if cfg.domain == _abi.CART_POLE else 3

@@ -449,6 +449,7 @@ struct orc_engine {
     int has_trace;
     double step_scale; /* 1/scale_div applied to every update (1.0 unless SHARED+MEAN) */
     double* s; int32_t* a; int32_t* ep; double* W; double* z; double* td; double* G;
+    double* W2; double* G2; /* second weight table of GreedyGQ (fa_td) / A2C (the policy's LFA) and its per-step dW accumulator */
     int32_t* n_ep; int32_t* last_len; uint64_t* len_hash;
     rsrl_stats_t st;
     double min_gap;
@@ -474,6 +475,8 @@ orc_engine_t* orc_engine_create(const rsrl_config_t* cfg) {
     e->ep = (int32_t*)calloc((size_t)e->N, sizeof(int32_t));
     e->W = (double*)calloc((size_t)wn, sizeof(double));
     e->G = (double*)calloc((size_t)(e->F * e->AW), sizeof(double));
+    e->W2 = (double*)calloc((size_t)wn, sizeof(double));
+    e->G2 = (double*)calloc((size_t)(e->F * e->AW), sizeof(double));
     e->z = e->has_trace ? (double*)calloc((size_t)(e->N * e->F * e->AW), sizeof(double)) : NULL;
     e->td = (double*)calloc((size_t)e->N, sizeof(double));
     e->n_ep = (int32_t*)calloc((size_t)e->N, sizeof(int32_t));
@@ -485,7 +488,7 @@ orc_engine_t* orc_engine_create(const rsrl_config_t* cfg) {
 
 void orc_engine_destroy(orc_engine_t* e) {
     if (!e) return;
-    free(e->s); free(e->a); free(e->ep); free(e->W); free(e->G); free(e->z); free(e->td);
+    free(e->s); free(e->a); free(e->ep); free(e->W); free(e->G); free(e->W2); free(e->G2); free(e->z); free(e->td);
     free(e->n_ep); free(e->last_len); free(e->len_hash); free(e);
 }
 
@@ -501,6 +504,7 @@ static void fresh_state(const orc_engine_t* e, int64_t g, int64_t t, double* s) 
 void orc_engine_reset(orc_engine_t* e, const double* init_states) {
     int64_t wn = e->F * e->AW * (e->cfg.weight_mode == RSRL_PER_ENV ? e->N : 1);
     memset(e->W, 0, (size_t)wn * sizeof(double)); /* LFA::vector => Array2::zeros (examples/q_learning.rs:25) */
+    memset(e->W2, 0, (size_t)wn * sizeof(double));
     if (e->z) memset(e->z, 0, (size_t)(e->N * e->F * e->AW) * sizeof(double));
     memset(e->td, 0, (size_t)e->N * sizeof(double));
     memset(e->ep, 0, (size_t)e->N * sizeof(int32_t));
@@ -535,12 +539,109 @@ static void accumulate_col(orc_engine_t* e, double* dst, int a, double coef, con
 /* One reference agent `handle(&Transition)` for env slot i (i < 0: stateless batch call, no traces).
  * W  = weights every evaluate() reads (W_t);  dst = where the update lands (W itself for PER_ENV /
  * N = 1 — exactly the reference — or the step's dW accumulator in SHARED mode). */
+/* softmax.rs:15-36,75-81: the policy's probabilities from its own LFA (theta) */
+static void gibbs_probs(const rsrl_config_t* c, const double* theta, int A, const double* s, double* p) {
+    double* h = evaluate_alloc(c, theta, A, s);
+    orc_policy_probs(RSRL_SOFTMAX, c->epsilon, h, A, p);
+    free(h);
+}
+
+/* GreedyGQ::handle — control/td/greedy_gq.rs:73-141.  fa_q = W (SGD lr), fa_td = W2 (SGD alpha). */
+static double greedy_gq_handle(orc_engine_t* e, const double* W, double* dst, const double* W2, double* dst2,
+                               const double* from, int a, double r, const double* to, int terminated) {
+    const rsrl_config_t* c = &e->cfg;
+    const int A = e->AW;
+    double* qs = evaluate_alloc(c, W, A, from);
+    double qsa = qs[a];                              /* :77 fa_q.evaluate_index((s,), a) */
+    double* vs = evaluate_alloc(c, W2, A, from);
+    double td_est = vs[a];                           /* :78 fa_td.evaluate((s, a)) */
+    double td_error;
+    free(qs); free(vs);
+    if (terminated) {
+        td_error = r - qsa;                          /* :81 */
+        double* phi = project_alloc(c, from);
+        accumulate_col(e, dst, a, (c->lr * td_error) / e->step_scale, phi);                /* :83-89 */
+        accumulate_col(e, dst2, a, (c->alpha * (td_error - td_est)) / e->step_scale, phi); /* :91-97 */
+        free(phi);
+    } else {
+        double* nq = evaluate_alloc(c, W, A, to);
+        double qnsna;
+        int na = orc_find_max(nq, A, &qnsna);        /* :107 */
+        free(nq);
+        td_error = r + c->gamma * qnsna - qsa;       /* :109 */
+        double* phi = project_alloc(c, from);
+        double* nphi = project_alloc(c, to);
+        accumulate_col(e, dst, a, (c->lr * td_error) / e->step_scale, phi);                /* :111-116 */
+        accumulate_col(e, dst, na, (c->lr * (-c->gamma * td_est)) / e->step_scale, nphi);  /* :117-124 */
+        accumulate_col(e, dst2, a, (c->alpha * (td_error - td_est)) / e->step_scale, phi); /* :127-133 */
+        free(phi); free(nphi);
+    }
+    return td_error;
+}
+
+/* One iteration of examples/a2c.rs:55-58: eval.handle(&t) (SARSA critic, control/td/sarsa.rs:53-75, with the Gibbs policy) then
+ * agent.handle(&t) (control/ac.rs:100-114 with the critic closure of a2c.rs:37-46 and Softmax::handle, softmax.rs:113-129,146-160).
+ * W = the critic's Q (SGD lr), W2 = the policy's LFA theta.  W_own / W2 are what evaluate() reads; in SHARED mode the critic
+ * closure sees W plus THIS transition's own critic update (for N = 1 that is exactly the reference's in-place update). */
+static double a2c_handle(orc_engine_t* e, int64_t g, uint64_t draw, const double* W, double* dst, const double* W2, double* dst2,
+                         const double* from, int a, double r, const double* to, int terminated) {
+    const rsrl_config_t* c = &e->cfg;
+    const int A = e->AW;
+    const int64_t F = e->F;
+    double* qs = evaluate_alloc(c, W, A, from);
+    double qsa = qs[a], residual;                    /* sarsa.rs:56 */
+    if (terminated) {
+        residual = r - qsa;                          /* sarsa.rs:58 */
+    } else {
+        uint32_t rnd[4]; int nf = 0;
+        double p[16];
+        orc_draw(c->seed, (uint64_t)g, draw, STREAM_TARGET, rnd);
+        gibbs_probs(c, W2, A, to, p);
+        double* h = evaluate_alloc(c, W2, A, to);
+        int na = orc_policy_sample(RSRL_SOFTMAX, c->epsilon, h, A, rnd, &nf); /* sarsa.rs:61 policy.sample(thread_rng, ns) */
+        free(h);
+        double* nq = evaluate_alloc(c, W, A, to);
+        residual = r + c->gamma * nq[na] - qsa;      /* sarsa.rs:62-64 */
+        free(nq);
+    }
+    double* phi = project_alloc(c, from);
+    const double cq = (c->lr * residual) / e->step_scale;
+    accumulate_col(e, dst, a, cq, phi);              /* sarsa.rs:67-73 -> SGD */
+    /* critic closure (a2c.rs:40-45) on the updated Q: only column a of Q(s) changed */
+    {
+        double acc = 0.0;
+        for (int64_t k = 0; k < F; ++k) acc = acc + phi[k] * (W[k * A + a] + cq * phi[k]);
+        qs[a] = acc;
+    }
+    double ps[16], ev = 0.0;
+    gibbs_probs(c, W2, A, from, ps);
+    for (int j = 0; j < A; ++j) ev = ev + qs[j] * ps[j];
+    const double adv = qs[a] - ev;
+    const double error = (c->alpha * adv) / e->step_scale;   /* ac.rs:109-113 */
+    /* Softmax::grad_log (softmax.rs:113-129): sf = pi(s); sf[a] -= 1; jac[:, col] = (-sf[col]) * phi; theta += error * jac (softmax.rs:146-160,
+     * ScaledGradientUpdate bypasses the optimiser) */
+    ps[a] = ps[a] - 1.0;
+    for (int col = 0; col < A; ++col)
+        for (int64_t k = 0; k < F; ++k) dst2[k * A + col] = dst2[k * A + col] + error * ((-ps[col]) * phi[k]);
+    free(phi); free(qs);
+    return residual;
+}
+
 static double agent_handle(orc_engine_t* e, int64_t i, int64_t g, uint64_t draw, const double* W, double* dst,
                            const double* from, int a, double r, const double* to, int terminated) {
     const rsrl_config_t* c = &e->cfg;
     const int A = e->AW;
     double residual, err;
     double* z = (e->has_trace && i >= 0) ? e->z + i * e->F * A : NULL;
+
+    if (c->algo == RSRL_GREEDY_GQ || c->algo == RSRL_A2C) {
+        const int per_env = c->weight_mode == RSRL_PER_ENV;
+        const int64_t off = per_env ? (W - e->W) : 0;
+        const double* W2 = e->W2 + off;
+        double* dst2 = per_env ? e->W2 + off : e->G2;
+        if (c->algo == RSRL_GREEDY_GQ) return greedy_gq_handle(e, W, dst, W2, dst2, from, a, r, to, terminated);
+        return a2c_handle(e, g, draw, W, dst, W2, dst2, from, a, r, to, terminated);
+    }
 
     if (c->algo == RSRL_TD0 || c->algo == RSRL_TD_LAMBDA) {
         /* prediction/td/td.rs:38-58, td_lambda.rs:44-77 */
@@ -650,6 +751,11 @@ static void env_step(orc_engine_t* e, int64_t i) {
     orc_draw(c->seed, (uint64_t)g, (uint64_t)e->t, STREAM_BEHAVIOUR, rnd);
     if (c->policy == RSRL_RANDOM || is_td_pred(c->algo)) {
         a = orc_policy_sample(RSRL_RANDOM, 0.0, NULL, e->A, rnd, &nf);
+    } else if (c->algo == RSRL_A2C) { /* agent.policy.sample(&mut rng, s): Gibbs over the policy's own LFA (a2c.rs:50,60) */
+        const double* W2 = c->weight_mode == RSRL_PER_ENV ? e->W2 + i * e->F * e->AW : e->W2;
+        double* h = evaluate_alloc(c, W2, e->AW, s);
+        a = orc_policy_sample(RSRL_SOFTMAX, c->epsilon, h, e->AW, rnd, &nf);
+        free(h);
     } else {
         double* q = evaluate_alloc(c, W, e->AW, s);
         a = orc_policy_sample(c->policy, c->epsilon, q, e->AW, rnd, &nf);
@@ -686,6 +792,7 @@ static void env_step(orc_engine_t* e, int64_t i) {
 
 void orc_engine_step_local(orc_engine_t* e, double* dW_out) {
     memset(e->G, 0, (size_t)(e->F * e->AW) * sizeof(double));
+    memset(e->G2, 0, (size_t)(e->F * e->AW) * sizeof(double));
     for (int64_t i = 0; i < e->N; ++i) env_step(e, i);
     if (dW_out) memcpy(dW_out, e->G, (size_t)(e->F * e->AW) * sizeof(double));
 }
@@ -694,6 +801,7 @@ void orc_engine_step_apply(orc_engine_t* e, const double* dW_sum) {
     if (e->cfg.weight_mode == RSRL_SHARED) {
         const double* g = dW_sum ? dW_sum : e->G;
         for (int64_t j = 0; j < e->F * e->AW; ++j) e->W[j] = e->W[j] + g[j];
+        for (int64_t j = 0; j < e->F * e->AW; ++j) e->W2[j] = e->W2[j] + e->G2[j];
     }
     e->t += 1;
     e->st.batch_steps += 1;
@@ -706,6 +814,7 @@ void orc_engine_step(orc_engine_t* e, int64_t k) {
 void orc_engine_handle(orc_engine_t* e, int64_t n, const double* from, const int32_t* actions, const double* rewards,
                        const double* to, const uint8_t* terminal, uint64_t draw, double* td_out) {
     memset(e->G, 0, (size_t)(e->F * e->AW) * sizeof(double));
+    memset(e->G2, 0, (size_t)(e->F * e->AW) * sizeof(double));
     for (int64_t i = 0; i < n; ++i) {
         int per_env = e->cfg.weight_mode == RSRL_PER_ENV;
         const double* W = per_env ? e->W + i * e->F * e->AW : e->W;
@@ -714,8 +823,60 @@ void orc_engine_handle(orc_engine_t* e, int64_t n, const double* from, const int
                                  actions[i], rewards[i], to + i * e->D, terminal[i]);
         if (td_out) td_out[i] = td;
     }
-    if (e->cfg.weight_mode == RSRL_SHARED)
+    if (e->cfg.weight_mode == RSRL_SHARED) {
         for (int64_t j = 0; j < e->F * e->AW; ++j) e->W[j] = e->W[j] + e->G[j];
+        for (int64_t j = 0; j < e->F * e->AW; ++j) e->W2[j] = e->W2[j] + e->G2[j];
+    }
+}
+
+void orc_engine_get_aux_weights(orc_engine_t* e, double* out) {
+    memcpy(out, e->W2, (size_t)(e->F * e->AW * (e->cfg.weight_mode == RSRL_PER_ENV ? e->N : 1)) * sizeof(double));
+}
+void orc_engine_set_aux_weights(orc_engine_t* e, const double* in) {
+    memcpy(e->W2, in, (size_t)(e->F * e->AW * (e->cfg.weight_mode == RSRL_PER_ENV ? e->N : 1)) * sizeof(double));
+}
+
+/* Domain::rollout (rsrl_domains/src/lib.rs:448-479) for env slot i of the engine's config with the engine's current weights held
+ * fixed.  pi = Policy::mode when greedy (greedy.rs:83: find_max; softmax.rs:141: argmax_first over the probabilities; A2C: the
+ * policy table) else Policy::sample with draw index draw + j.  Returns Trajectory::n_transitions(). */
+int64_t orc_engine_rollout(orc_engine_t* e, int64_t i, const double* init_state, int64_t step_limit, int greedy, uint64_t draw,
+                           double* start_out, double* next_out, int32_t* actions_out, double* rewards_out, uint8_t* terminal_out) {
+    const rsrl_config_t* c = &e->cfg;
+    const int64_t g = c->env_offset + i;
+    const double* Wq = c->weight_mode == RSRL_PER_ENV ? e->W + i * e->F * e->AW : e->W;
+    const double* Wp = c->algo == RSRL_A2C ? (c->weight_mode == RSRL_PER_ENV ? e->W2 + i * e->F * e->AW : e->W2) : Wq;
+    const int policy = c->algo == RSRL_A2C ? RSRL_SOFTMAX : c->policy;
+    const int64_t tmax = step_limit > 0 ? (step_limit - 1 > 1 ? step_limit - 1 : 1) : -1;
+    const int64_t take = step_limit > 0 ? (step_limit - 1 > 0 ? step_limit - 1 : 0) : -1; /* iter.take(sl.saturating_sub(1)) */
+    double s[RSRL_MAX_DIM];
+    int64_t n = 0;
+    int terminated = 0;
+    if (init_state) memcpy(s, init_state, (size_t)e->D * sizeof(double));
+    else fresh_state(e, g, (int64_t)draw, s);
+    memcpy(start_out, s, (size_t)e->D * sizeof(double)); /* let start = self.emit() */
+    for (int64_t j = 0;; ++j) {
+        if (j > 0 && terminated) break;                 /* successors: Observation::Terminal => None */
+        if (take >= 0 && j >= take && !(j == 0)) break; /* .take(sl - 1): the first step below is executed even when it is not recorded */
+        double* q = evaluate_alloc(c, Wp, e->AW, s);
+        int a, nf = 0;
+        if (greedy) {
+            if (policy == RSRL_SOFTMAX) { double p[16]; orc_policy_probs(RSRL_SOFTMAX, c->epsilon, q, e->AW, p); a = orc_argmax_first(p, e->AW, NULL); }
+            else a = orc_find_max(q, e->AW, NULL);
+        } else {
+            uint32_t rnd[4];
+            orc_draw(c->seed, (uint64_t)g, draw + (uint64_t)j, STREAM_BEHAVIOUR, rnd);
+            a = orc_policy_sample(policy, c->epsilon, q, e->AW, rnd, &nf);
+        }
+        free(q);
+        double r;
+        orc_domain_step(c->domain, s, a, &r, &terminated);
+        if (take >= 0 && j >= take) break;              /* step_limit == 1: executed, not recorded (lib.rs:472-476) */
+        memcpy(next_out + j * e->D, s, (size_t)e->D * sizeof(double));
+        actions_out[j] = a; rewards_out[j] = r; terminal_out[j] = (uint8_t)terminated;
+        n = j + 1;
+        if (tmax >= 0 && n >= tmax && take >= 0 && n >= take) break;
+    }
+    return n;
 }
 
 void orc_engine_get_states(orc_engine_t* e, double* out) { memcpy(out, e->s, (size_t)(e->N * e->D) * sizeof(double)); }

@@ -73,6 +73,10 @@ void orc_engine_get_actions(orc_engine_t* e, int32_t* out);
 void orc_engine_get_episode_steps(orc_engine_t* e, int32_t* out);
 void orc_engine_get_weights(orc_engine_t* e, double* out);
 void orc_engine_set_weights(orc_engine_t* e, const double* in);
+void orc_engine_get_aux_weights(orc_engine_t* e, double* out); /* GreedyGQ fa_td / A2C policy LFA */
+void orc_engine_set_aux_weights(orc_engine_t* e, const double* in);
+int64_t orc_engine_rollout(orc_engine_t* e, int64_t i, const double* init_state, int64_t step_limit, int greedy, uint64_t draw,
+                           double* start_out, double* next_out, int32_t* actions_out, double* rewards_out, uint8_t* terminal_out);
 void orc_engine_get_traces(orc_engine_t* e, double* out);
 void orc_engine_set_traces(orc_engine_t* e, const double* in);
 void orc_engine_get_td_errors(orc_engine_t* e, double* out);

@@ -202,7 +202,7 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, 1, 1, 1, 1, 4, 0, 0, 0u};
+    SyncArgs sync = {nullptr, 1, 1, 1, 1, 4, 0, 0, 0u, 0, 1, 0, 0, nullptr, nullptr};
     size_t stage_bytes = 0;
     uint32_t xepoch = 0;  // exchange epoch: counts batched steps over the engine's life, NOT reset by rsrl_engine_reset
     int pcap = 0;  // padded slot count of the CTA reduce buffers
@@ -283,9 +283,15 @@ static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
     const int cap = lpg * seg_len;
     const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;
     const size_t nvp = (size_t)persist_nvp((int)e->FA, (int)e->rsz);
-    const size_t elems = (size_t)(2 + cs) * nvp + (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap;
-    const size_t bytes = 16 + elems * e->rsz;
+    const size_t ncl = (size_t)(grid / cs);
+    const size_t elems = (size_t)(2 + cs + (!e->sync.fx && ncl > 1 ? ncl : 0)) * nvp + (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap;
+    size_t bytes = 16 + elems * e->rsz;
+    if (e->sync.fx) bytes += (size_t)4 * ((e->FA + 1) / 2 * 2) * sizeof(long long);  // running sums of the counting exchange
     if (bytes > 220 * 1024) return false;
+    // small blocks: two CTAs would fit on one SM (registers and shared memory) and the cluster scheduler may pair them up while other SMs
+    // stay empty; asking for more than half of an SM's shared memory keeps it at one CTA per SM.  Not for large blocks: their register
+    // spills (~200 B per thread) live in L1, and a larger shared-memory carve-out pushes them out to L2 (measured: +27 % step time).
+    if (grid > 1 && block <= 256 && bytes < 116 * 1024) bytes = 116 * 1024;
     e->pcap = cap;
     e->sync.lpr = lpr; e->sync.lpg = lpg; e->sync.seg_len = seg_len;
     e->sync.cluster_size = cs; e->sync.n_clusters = grid / cs;
@@ -314,9 +320,20 @@ static void choose_persistent(rsrl_engine* e) {
     e->sync.debug_skip = getenv("RSRL_B200_DEBUG_SKIP") ? atoi(getenv("RSRL_B200_DEBUG_SKIP")) : 0;
     int g0 = (int)((e->N + 127) / 128);
     if (g0 > sms) g0 = sms;
-    // cluster size: 8 (portable maximum) packs 16 clusters = 128 CTAs on a B200 (8 GPCs of 16-20 SMs); RSRL_B200_CLUSTER overrides
-    int cs = getenv("RSRL_B200_CLUSTER") ? atoi(getenv("RSRL_B200_CLUSTER")) : 8;
-    if (cs < 1 || cs > kMaxClusterSize || (cs & (cs - 1))) cs = 8;
+    // fp32: the counting exchange (persistent.cuh), one L2 hop, no clusters: all SMs take part.  f64 engines: cluster + LL-line exchange.
+    e->sync.fx = e->cfg.dtype == RSRL_F32 ? 1 : 0;
+    e->sync.nsub = getenv("RSRL_B200_NSUB") ? atoi(getenv("RSRL_B200_NSUB")) : 1;  // sub-tables (measured: more tables = more polls = slower)
+    if (e->sync.nsub != 1 && e->sync.nsub != 2 && e->sync.nsub != 4) e->sync.nsub = 1;
+    // first poll 400 ns after the reductions were issued: earlier polls only queue in front of them in L2 (measured, profiles/r02_persistent.md)
+    e->sync.poll_delay_ns = getenv("RSRL_B200_POLL_DELAY") ? atoi(getenv("RSRL_B200_POLL_DELAY")) : 400;
+    e->sync.poll_backoff_ns = getenv("RSRL_B200_POLL_BACKOFF") ? atoi(getenv("RSRL_B200_POLL_BACKOFF")) : 0;
+    if (g0 > 255) g0 = 255;  // the arrival count of one step has to fit the low byte of an accumulator word
+    // cluster size 4: a B200 (8 GPCs of 16-20 SMs) holds 33 such clusters = 132 CTAs at one CTA per SM, so the 65 536 envs of
+    // BASELINE configs[1] still get one thread each (497 per CTA); size 8 only packs 15 clusters = 120 CTAs (547 envs per CTA:
+    // two passes per step), size 16 packs 7.  Measured (profiles/r02_persistent.md).  RSRL_B200_CLUSTER overrides.
+    int cs = getenv("RSRL_B200_CLUSTER") ? atoi(getenv("RSRL_B200_CLUSTER")) : 4;
+    if (cs < 1 || cs > kMaxClusterSize || (cs & (cs - 1))) cs = 4;
+    if (e->sync.fx) cs = 1;
     if (g0 == 1) cs = 1;
     int grid = (g0 + cs - 1) / cs * cs;
     if (!persistent_shape(e, grid, cs)) return;
@@ -462,8 +479,8 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
         cudaMemcpy(h.data(), e->phase_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         const char* names_d[8] = {"dW: inputs -> u, v (regs)", "dW: wait MMA (buffer free)", "dW: split + scalar stores", "dW: fence + __syncthreads",
                                   "dW: MMA issue (thread 0)", "-", "-", "-"};
-        const char* names_p[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "LL exchange (thread 0)", "wait LL (bar)",
-                                  "  LL: sum segs + publish 1", "  LL: leader hop-1 gather", "  LL: leader sum + publish 2"};
+        const char* names_p[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "exchange: rest (member: all)", "final bar",
+                                  "leader: wait members (hop A)", "leader: sum + hops N/B", "-"};
         const char* names_t[8] = {"load + tables", "unit compute (regs)", "wait MMA (mbarrier)", "contract (LDTM + FMA)", "store unit + sync + issue",
                                   "TD + stores + bookkeeping", "issuer: MMA issue (pipe busy)", "issuer: idle (no unit ready)"};
         const char** names = e->f4tc ? names_t : names_p;
@@ -483,7 +500,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (int r = 0; r < kMaxRanks; ++r) if (e->peer_mapped[r]) cudaIpcCloseMemHandle(e->peer_mapped[r]);
     void* bufs[] = {e->states, e->actions, e->ep_steps, e->n_ep, e->last_len, e->len_hash, e->td, e->W, e->z,
-                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage, e->inbox, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef, e->f4args.tabs, e->f4args.q, e->f4args.aux, e->f4args.next_states};
+                    e->partials, e->dW, e->counters, e->stage, e->init_bounds, e->sync.stage, e->inbox, e->sync.acc, e->sync.prev, e->targs.G, e->targs.barrier, e->f4args.from_states, e->f4args.coef, e->f4args.tabs, e->f4args.q, e->f4args.aux, e->f4args.next_states};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -608,6 +625,14 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         E_TRY(cudaMalloc(&e->sync.stage, e->stage_bytes));
         E_TRY(cudaMemset(e->sync.stage, 0, e->stage_bytes));                       // epoch 0 is never published
         e->inbox_bytes = (size_t)2 * kMaxRanks * e->sync.n_clusters * e->FA * (e->rsz / 4) * sizeof(uint2);
+        if (e->sync.fx) {  // counting exchange: local table, running sums, and the world table in the peer-visible mailbox
+            const size_t tab = (size_t)2 * e->FA * kAccStride * sizeof(unsigned long long);
+            E_TRY(cudaMalloc(&e->sync.acc, tab * e->sync.nsub));
+            E_TRY(cudaMemset(e->sync.acc, 0, tab * e->sync.nsub));
+            E_TRY(cudaMalloc(&e->sync.prev, (size_t)4 * e->FA * sizeof(long long)));
+            E_TRY(cudaMemset(e->sync.prev, 0, (size_t)4 * e->FA * sizeof(long long)));
+            e->inbox_bytes = tab;
+        }
         E_TRY(cudaMalloc(&e->inbox, e->inbox_bytes));
         E_TRY(cudaMemset(e->inbox, 0, e->inbox_bytes));
     }
@@ -746,7 +771,8 @@ int rsrl_engine_sync(rsrl_engine_t* e) {
     Counters c;
     CU_TRY(cudaMemcpy(&c, e->counters, sizeof c, cudaMemcpyDeviceToHost));
     if (c.pad) return fail(RSRL_ECUDA, "tensor-core pipeline fault: a tcgen05 completion barrier timed out (f4tc.cuh)");
-    if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum (NaN weights); the reference panics in utils.rs:76");
+    if (c.nonfinite) return fail(RSRL_ENONFINITE, "a Q vector had no valid maximum (NaN weights; the reference panics in utils.rs:76), or a weight update "
+                                                  "left the range of the fp32 exchange (|per-CTA dW| >= 16384: the run is diverging)");
     return RSRL_OK;
 }
 
@@ -973,13 +999,13 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
 }
 
 // ---- introspection used by the parity tests ----
-int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[16]) {
+int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[24]) {
     if (!e || !out) return fail(RSRL_EINVAL, "null argument");
-    memset(out, 0, 16 * sizeof(int32_t));
+    memset(out, 0, 24 * sizeof(int32_t));
     out[0] = e->persistent ? 1 : 0; out[1] = e->pmode; out[2] = e->pgrid; out[3] = e->sync.cluster_size; out[4] = e->sync.n_clusters;
     out[5] = e->pblock; out[6] = e->sync.lpr; out[7] = e->sync.lpg; out[8] = e->sync.seg_len; out[9] = e->sync.pe_smem;
     out[10] = e->world; out[11] = e->rank; out[12] = e->peers_attached ? 1 : 0; out[13] = (int32_t)e->psmem;
-    out[14] = e->tile ? 1 : 0; out[15] = e->f4 ? (1 + e->f4tc) : 0;
+    out[14] = e->tile ? 1 : 0; out[15] = e->f4 ? (1 + e->f4tc) : 0; out[16] = e->sync.fx;
     return RSRL_OK;
 }
 

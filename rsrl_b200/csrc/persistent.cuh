@@ -10,16 +10,27 @@
 //             they evaluate Q(s_t), and their scaled TD error per action column.  A reducer thread owns
 //             4 rows x one slot segment (one load of the TD errors feeds 4 rows), a shuffle butterfly
 //             over the segment lanes finishes the CTA partial (`part`, NV values in shared memory).
-//   hop A   : (cluster, DSMEM) every member CTA copies its partial into the cluster leader's shared memory
-//             with ONE cp.async.bulk (shared::cta -> shared::cluster) that completes on the leader's mbarrier;
+//   hop A   : (cluster, DSMEM) every member CTA stores its partial into the cluster leader's shared memory with
+//             st.async (16 bytes per thread, shared::cluster) that complete on the leader's mbarrier (complete_tx);
 //             the leader sums the partials in rank order.  No polling: the waiters sleep on the mbarrier.
 //   hop N   : (multi-GPU, NVLink) leader c of every GPU stores its cluster partial as 8-byte LL words
 //             {payload, epoch} into slot (rank, c) of EVERY GPU's inbox through cudaIpc-mapped peer pointers and
 //             sums the world's slot-c partials from its own inbox — all leaders of all GPUs in parallel.
 //   hop B   : (L2) the leaders exchange their (world-)cluster partials as 16-byte LL lines {3 payload words,
 //             epoch}; lane l of a row polls clusters l, l + lpr, ...; a butterfly gives the total.
-//   hop C   : (cluster, DSMEM) the leader copies the total into every member's shared memory (cp.async.bulk +
-//             the member's mbarrier); every CTA applies W += total to its own copy of W.
+//   hop C   : (cluster, DSMEM) the leader stores the total into every member's shared memory (st.async + the
+//             member's mbarrier); every CTA applies W += total to its own copy of W.
+//
+// fp32 engines (the bench dtype) use a shorter exchange instead of hops A-C — COUNTING ACCUMULATORS in L2:
+//   every CTA converts its partial to 2^-40 fixed point and adds (value << 8) + 1 to NV 64-bit words with relaxed
+//   reductions (red.add.u64): the low byte counts arrivals, the upper 56 bits are a running (never reset, wrapping) sum.
+//   Every CTA polls the NV words until the count says that all G partials of this step are in, and takes the difference
+//   to the running sum it saw at the previous completion.  Data and flag share one naturally atomic 64-bit word (no
+//   fence, no 16-byte assumption), integer addition is order independent (any arrival order gives the same bits), two
+//   tables alternate by step parity so that a fast CTA's next-step contribution cannot overtake a slow reader, and the
+//   whole exchange is ONE L2 hop.  Multi-GPU: CTA 0 forwards the GPU's total to every GPU's world table through NVLink
+//   peer pointers (red.add.u64 at system scope) and every CTA polls the world table instead.
+//   Measured against the cluster exchange in profiles/r02_persistent.md.
 //
 // Every CTA of every GPU performs the same additions in the same order, so all W copies stay bit-identical;
 // the order is restated on the host by oracle/oracle32.cpp (bit-exact parity of the fp32 path).
@@ -34,6 +45,9 @@ constexpr int kModeSharedTrace = 2;  // internal MODE: SHARED weights + per-env 
 constexpr int kMaxRanks = 8;
 constexpr int kMaxClusters = 64;     // leaders that exchange through L2
 constexpr int kMaxClusterSize = 16;
+constexpr int kAccStride = 16;       // 64-bit words between two accumulators: one 128-byte line each (atomics on one line serialise)
+constexpr double kFxScale = 1099511627776.0;   // 2^40: fixed-point unit of the counting exchange
+constexpr float kFxLimit = 16384.0f;           // |CTA partial| must stay below 2^14 (2^54 in fixed point; the field has 56 bits)
 
 struct SyncArgs {
     uint4* stage;   // [2][n_clusters][ROWS * LPW]   (world-)cluster partial rows (parity double-buffered)
@@ -45,12 +59,20 @@ struct SyncArgs {
     int pe_smem;    // PER_ENV: keep every env's own W (F*A values, column `tid`) in shared memory for the whole launch
     int debug_skip; // development timing aid (RSRL_B200_DEBUG_SKIP): bit 0 skips the grid exchange, bit 1 the CTA reduce (wrong results)
     uint32_t epoch_base;  // exchange epoch before the launch's first step (monotonic over the engine's life, never reset)
+    // fp32 exchange through counting accumulators in L2 (see the header comment); fx == 0: the cluster + LL-line exchange
+    int fx;
+    int nsub;                 // sub-tables per parity (1, 2 or 4)
+    int poll_delay_ns;        // pause between the reductions and the first poll / between two polls: polls that come before the last
+    int poll_backoff_ns;      // partial has landed only queue in front of the reductions in L2
+    unsigned long long* acc;  // [2][nsub][NV][kAccStride] running fixed-point sums of the CTA partials + arrival count in the low byte (parity double-buffered)
+    long long* prev;          // [4][NV] running sums at the previous completion: acc parity 0, 1, world table parity 0, 1 (written at kernel end)
 };
 
 // Cross-GPU exchange (one process per GPU): every rank owns an inbox of 8-byte LL words
 // {payload, epoch} that its peers write through NVLink (cudaIpc-mapped pointers).
 struct PeerArgs {
-    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox [2][world][n_clusters][NV * WPV] as seen from this GPU
+    uint2* inbox[kMaxRanks];  // inbox[r]: rank r's mailbox as seen from this GPU.  LL exchange: [2][world][n_clusters][NV * WPV] 8-byte LL words;
+                              // counting exchange (fp32): the rank's world table [2][NV][kAccStride] of 64-bit accumulators
     int rank, world;
 };
 
@@ -74,6 +96,38 @@ __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
 __device__ __forceinline__ void st_ll(uint4* p, uint32_t a, uint32_t b, uint32_t c, uint32_t epoch) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(epoch) : "memory");
 }
+
+// ---- counting accumulators: value and arrival count in ONE 64-bit word, added with relaxed reductions ----
+__device__ __forceinline__ void red_add_u64_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_u64_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// fp32 <-> the 2^-40 fixed-point grid (one rounding each way; identical on the host: oracle/oracle32.cpp)
+__host__ __device__ __forceinline__ long long fx_from_float(float x) {
+#ifdef __CUDA_ARCH__
+    return __double2ll_rn((double)x * kFxScale);
+#else
+    return (long long)llrint((double)x * kFxScale);
+#endif
+}
+__host__ __device__ __forceinline__ float fx_to_float(long long q) { return (float)((double)q * (1.0 / kFxScale)); }
+// the word holds (sum << 8) + count (mod 2^64): take `count` contributions off and read the 56-bit running sum
+__host__ __device__ __forceinline__ long long fx_running_sum(unsigned long long word, unsigned long long count) {
+    return (long long)(word - count) >> 8;
+}
+__host__ __device__ __forceinline__ long long fx_sext56(long long v) { return (long long)((unsigned long long)v << 8) >> 8; }
 
 // ---- thread-block cluster / DSMEM primitives ----
 __device__ __forceinline__ uint32_t cl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +158,12 @@ __device__ __forceinline__ void cl_bulk_copy(uint32_t dst_cluster_addr, uint32_t
                  ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cl_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16 bytes from registers to the shared memory of another CTA of the cluster; counts 16 bytes on that CTA's mbarrier.
+// Latency of a DSMEM store (~250 cycles); a bulk copy of the same data goes through the copy engine and costs several times that.
+__device__ __forceinline__ void cl_st_async16(uint32_t dst_cluster_addr, uint4 v, uint32_t mbar_cluster_addr) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr) : "memory");
+}
 
 // A "row" carries NV <= 3 values.  fp32: one 16-byte LL line {v0, v1, v2, epoch}; fp64: one line per value.
 template <typename R, int NV> struct LLRow;
@@ -145,25 +205,26 @@ template <int NV> struct LLRow<double, NV> {
     }
 };
 
-// acc = sum of the rows published by producers m = first, first + step, ... (< cnt) at base + m * stride;
-// two producers are polled at a time so that their L2 round trips overlap.
+// acc = sum, in the order m = first, first + step, ... (< cnt), of the rows published at base + m * stride.
+// Up to MAXO lines are requested before the first one is checked, so that their L2 round trips overlap.
 template <typename R, int NV>
 __device__ __forceinline__ void ll_gather(const uint4* base, size_t stride, int first, int step, int cnt, uint32_t epoch, bool valid, R* acc) {
     using LR = LLRow<R, NV>;
+    constexpr int MAXO = LR::LPW == 1 ? 5 : 2;
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc[c] = (R)0;
     if (!valid) return;
-    for (int m = first; m < cnt; m += 2 * step) {
-        const int m2 = m + step;
-        const bool two = m2 < cnt;
-        uint4 w0[LR::LPW], w1[LR::LPW];
-        LR::load(base + (size_t)m * stride, w0);
-        if (two) LR::load(base + (size_t)m2 * stride, w1);
-        while (!LR::ready(w0, epoch)) LR::load(base + (size_t)m * stride, w0);
-        LR::add(w0, acc);
-        if (two) {
-            while (!LR::ready(w1, epoch)) LR::load(base + (size_t)m2 * stride, w1);
-            LR::add(w1, acc);
+    for (int m0 = first; m0 < cnt; m0 += MAXO * step) {
+        uint4 w[MAXO][LR::LPW];
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o)
+            if (m0 + o * step < cnt) LR::load(base + (size_t)(m0 + o * step) * stride, w[o]);
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) {
+            if (m0 + o * step < cnt) {
+                while (!LR::ready(w[o], epoch)) LR::load(base + (size_t)(m0 + o * step) * stride, w[o]);
+                LR::add(w[o], acc);
+            }
         }
     }
 }
@@ -201,7 +262,11 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     constexpr int NDC = TRACE ? 1 : AW;                     // values per row = rows of scaled TD errors
     constexpr int NV = ROWS * NDC;                          // values of one dW partial (= F*A), index row * NDC + c == the flat F x A index
     constexpr int NVP = persist_nvp(NV, (int)sizeof(R));
-    constexpr uint32_t NVB = NVP * sizeof(R);               // bytes of one partial (multiple of 16: bulk copies)
+    constexpr uint32_t NVB = NVP * sizeof(R);               // bytes of one partial (multiple of 16)
+    constexpr int NCH = (int)(NVB / 16);                    // 16-byte chunks of one partial (one st.async each)
+    constexpr bool FX = sizeof(R) == 4;                     // fp32: counting exchange; f64: cluster + LL lines (each instantiation carries one)
+    constexpr int MAXSUB = 4;                               // sub-tables of the counting exchange (CTA b adds to sub-table b % nsub)
+    constexpr int NVP8 = (NV + 1) / 2 * 2;                  // prevs rows (long long), padded to 16 bytes
     constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
     constexpr int FApad = F * WS;
     using LR = LLRow<R, NDC>;
@@ -234,12 +299,18 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     R* Wsm = inbuf + (size_t)CS * NVP;        // [FApad]
     R* red = Wsm + FApad;                     // [ROWSP][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
     R* dcs = red + (size_t)ROWSP * cap;       // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
+    R* gath = dcs + (size_t)NDC * cap;        // [n_clusters][NVP] leader: the clusters' partials gathered from L2 (only when n_clusters > 1)
+    // counting exchange: running sums seen at the previous completion [4][NVP8] (local parity 0, 1; world parity 0, 1); it takes gath's place
+    long long* prevs = reinterpret_cast<long long*>(gath);
     const uint32_t mb_in = cl_smem_u32(&mbars[0]), mb_tot = cl_smem_u32(&mbars[1]);
 
     if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
         for (int j = tid; j < (ROWSP + NDC) * cap; j += BLOCK) red[j] = (R)0;
         for (int j = tid; j < NVP; j += BLOCK) { part[j] = (R)0; totbuf[j] = (R)0; }
+        if (FX) {
+            for (int j = tid; j < 4 * NV; j += BLOCK) prevs[(j / NV) * NVP8 + j % NV] = sy.prev[j];
+        }
         if (CS > 1) {
             if (tid == 0) {
                 cl_mbar_init(mb_in, 1);
@@ -285,8 +356,14 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const bool row_valid = SHAREDW && row < ROWS;
     const bool warp_rows = SHAREDW && (tid & ~31) < ROWS * lpr;  // warp-uniform: this warp owns at least one row
 
+    // phase profile (RSRL_B200_PHASE_PROFILE=1): thread 0 adds its cycle counts straight to global memory — no counters in registers
     const bool prof = a.phase_prof != nullptr && tid == 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, c1 = 0;
+    long long c0 = 0;
+    auto tick = [&](int q) {
+        const long long c1 = clock64();
+        a.phase_prof[b * 8 + q] += c1 - c0;
+        c0 = c1;
+    };
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
         if (prof) c0 = clock64();
@@ -394,7 +471,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     for (int d = 0; d < D; ++d) a.states[i * D + d] = s[d];
                 }
             }
-            if (prof) { c1 = clock64(); pc[0] += c1 - c0; c0 = c1; }
+            if (prof) tick(0);
             if (SHAREDW) {
                 if (TRACE) {
                     dcs[tid] = active ? o.coef : (R)0;
@@ -404,7 +481,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 }
                 // (a slot idle in this chunk keeps a stale but finite row; its dcs entries are 0)
                 __syncthreads();
-                if (prof) { c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
+                if (prof) tick(1);
                 if (reducer && !(sy.debug_skip & 2)) {
                     const int s0 = rseg * seg_len;
                     const R* prow = red + (size_t)(rg * RPT) * cap + s0;
@@ -449,18 +526,82 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 }
             }
             __syncthreads();
-            if (prof) { c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
+            if (prof) tick(2);
             const uint32_t epoch = sy.epoch_base + (uint32_t)step + 1u;
             const int par = (int)(epoch & 1u);
             const uint32_t ph = (uint32_t)(step & 1);  // one mbarrier completion per step
             const R* total = part;                     // one CTA (or exchange skipped): its partial is the total
+            if constexpr (FX) {
+              if ((G > 1 || pe.world > 1) && !(sy.debug_skip & 1)) {
+                // ---- counting accumulators (fp32): one L2 hop ----
+                const int p = par;
+                const unsigned long long k = ((unsigned long long)epoch + (unsigned long long)p) >> 1;  // steps of this parity so far, this one included
+                const bool multi = pe.world > 1;
+                const int nsub = sy.nsub;  // CTA b adds into sub-table b % nsub: fewer same-address reductions queue up in L2
+                unsigned long long* accp = sy.acc + (size_t)p * nsub * NV * kAccStride;
+                {
+                    unsigned long long* mine = accp + (size_t)(b % nsub) * NV * kAccStride;
+                    for (int j = tid; j < NV; j += BLOCK) {
+                        float x = (float)part[j];
+                        if (!(fabsf(x) < kFxLimit)) { atomicExch(&a.counters->nonfinite, 1); x = 0.0f; }  // NaN / Inf / beyond the fixed-point range
+                        red_add_u64_gpu(mine + (size_t)j * kAccStride, ((unsigned long long)fx_from_float(x) << 8) + 1ull);
+                    }
+                }
+                if (sy.poll_delay_ns > 0) __nanosleep((unsigned)sy.poll_delay_ns);
+                if (!multi || b == 0) {
+                    for (int j = tid; j < NV; j += BLOCK) {
+                        unsigned long long w[MAXSUB];
+#pragma unroll
+                        for (int q = 0; q < MAXSUB; ++q)
+                            if (q < nsub) w[q] = ld_u64_gpu(accp + ((size_t)q * NV + j) * kAccStride);
+                        long long sum = 0;
+#pragma unroll
+                        for (int q = 0; q < MAXSUB; ++q) {
+                            if (q < nsub) {
+                                const unsigned long long cnt = (unsigned long long)((G - q + nsub - 1) / nsub) * k;  // CTAs q, q + nsub, ... over k steps
+                                const unsigned long long* word = accp + ((size_t)q * NV + j) * kAccStride;
+                                while ((w[q] & 0xFFull) != (cnt & 0xFFull)) {
+                                    if (sy.poll_backoff_ns > 0) __nanosleep((unsigned)sy.poll_backoff_ns);
+                                    w[q] = ld_u64_gpu(word);
+                                }
+                                sum += fx_running_sum(w[q], cnt);
+                            }
+                        }
+                        const long long dq = fx_sext56(sum - prevs[p * NVP8 + j]);
+                        prevs[p * NVP8 + j] = sum;
+                        if (!multi) {
+                            Wsm[(j / AW) * WS + j % AW] += (R)fx_to_float(dq);
+                        } else {  // CTA 0 forwards this GPU's total to every GPU's world table
+                            for (int r = 0; r < pe.world; ++r)
+                                red_add_u64_sys(reinterpret_cast<unsigned long long*>(pe.inbox[r]) + ((size_t)p * NV + j) * kAccStride,
+                                                ((unsigned long long)dq << 8) + 1ull);
+                        }
+                    }
+                }
+                if (multi) {
+                    const unsigned long long cnt = (unsigned long long)pe.world * k;
+                    const unsigned long long* wtab = reinterpret_cast<const unsigned long long*>(pe.inbox[pe.rank]) + (size_t)p * NV * kAccStride;
+                    for (int j = tid; j < NV; j += BLOCK) {
+                        const unsigned long long* word = wtab + (size_t)j * kAccStride;
+                        unsigned long long w = ld_u64_sys(word);
+                        while ((w & 0xFFull) != (cnt & 0xFFull)) w = ld_u64_sys(word);
+                        const long long sum = fx_running_sum(w, cnt);
+                        const long long dq = fx_sext56(sum - prevs[(2 + p) * NVP8 + j]);
+                        prevs[(2 + p) * NVP8 + j] = sum;
+                        Wsm[(j / AW) * WS + j % AW] += (R)fx_to_float(dq);
+                    }
+                }
+              } else {
+                for (int j = tid; j < NV; j += BLOCK) Wsm[(j / AW) * WS + j % AW] += part[j];
+              }
+            } else {
             if ((G > 1 || pe.world > 1) && !(sy.debug_skip & 1)) {
                 if (!leader) {
                     // hop A (send): my partial -> the leader's inbuf[crank]; then sleep until the total arrives (hop C)
-                    if (tid == 0) {
-                        cl_mbar_expect_tx(mb_tot, NVB);
-                        cl_fence_async();
-                        cl_bulk_copy(cl_mapa(cl_smem_u32(inbuf + (size_t)crank * NVP), 0), cl_smem_u32(part), NVB, cl_mapa(mb_in, 0));
+                    if (tid == 0) cl_mbar_expect_tx(mb_tot, NVB);
+                    for (int j = tid; j < NCH; j += BLOCK) {  // 16 bytes per thread, straight from `part` (complete after the barrier above)
+                        const uint4 v = reinterpret_cast<const uint4*>(part)[j];
+                        cl_st_async16(cl_mapa(cl_smem_u32(inbuf + (size_t)crank * NVP) + 16u * (uint32_t)j, 0), v, cl_mapa(mb_in, 0));
                     }
                     cl_mbar_wait(mb_tot, ph);
                 } else {
@@ -469,6 +610,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         if (tid == 0) cl_mbar_expect_tx(mb_in, (uint32_t)(CS - 1) * NVB);
                         cl_mbar_wait(mb_in, ph);
                     }
+                    if (prof) tick(5);  // leader: members' partials arrived (hop A + skew between the cluster's CTAs)
                     for (int j = tid; j < NV; j += BLOCK) {
                         R acc = part[j];
                         for (int r = 1; r < CS; ++r) acc += inbuf[(size_t)r * NVP + j];
@@ -523,12 +665,52 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
 #pragma unroll
                                 for (int c = 0; c < NDC; ++c) dW[c] = tot[c];
                             }
+                            if (NCL > 1 && row_valid && rl == 0) {
+                                // hop B (L2), publish: my (world-)cluster partial as LL lines {payload, epoch}
+                                LR::publish(sy.stage + ((size_t)par * NCL + cid) * ((size_t)ROWS * LPW) + (size_t)row * LPW, dW, epoch);
+                            }
+                        }
+                        if (NCL > 1) {
+                            // hop B, gather: ALL threads of the leader poll (<= 3 lines each, all requested before the first is checked: one
+                            // L2 round trip) and drop the payloads into shared memory ...
+                            const size_t rstride = (size_t)ROWS * LPW;  // lines between two producers
+                            const uint4* st = sy.stage + (size_t)par * NCL * rstride;
+                            constexpr int MAXL = 3;
+                            for (int q0 = tid; q0 < ROWS * NCL; q0 += MAXL * BLOCK) {
+                                uint4 w[MAXL][LPW];
+#pragma unroll
+                                for (int o = 0; o < MAXL; ++o) {
+                                    const int q = q0 + o * BLOCK;
+                                    if (q < ROWS * NCL) LR::load(st + (size_t)(q / ROWS) * rstride + (size_t)(q % ROWS) * LPW, w[o]);
+                                }
+#pragma unroll
+                                for (int o = 0; o < MAXL; ++o) {
+                                    const int q = q0 + o * BLOCK;
+                                    if (q < ROWS * NCL) {
+                                        const uint4* line = st + (size_t)(q / ROWS) * rstride + (size_t)(q % ROWS) * LPW;
+                                        while (!LR::ready(w[o], epoch)) LR::load(line, w[o]);
+                                        R v[NDC];
+#pragma unroll
+                                        for (int c = 0; c < NDC; ++c) v[c] = (R)0;
+                                        LR::add(w[o], v);
+#pragma unroll
+                                        for (int c = 0; c < NDC; ++c) gath[(size_t)(q / ROWS) * NVP + (q % ROWS) * NDC + c] = v[c];
+                                    }
+                                }
+                            }
+                            __syncthreads();
+                        }
+                        if (warp_rows) {
                             if (NCL > 1) {
-                                // hop B (L2): publish my (world-)cluster partial, gather every cluster's: lane l <-> clusters l, l + lpr, ...
-                                const size_t rstride = (size_t)ROWS * LPW;  // lines between two producers
-                                uint4* st = sy.stage + (size_t)par * NCL * rstride;
-                                if (row_valid && rl == 0) LR::publish(st + (size_t)cid * rstride + (size_t)row * LPW, dW, epoch);
-                                ll_gather<R, NDC>(st + (size_t)row * LPW, rstride, rl, lpr, NCL, epoch, row_valid, dW);
+                                // ... where lane l of a row sums clusters l, l + lpr, ... in order; a butterfly over the lanes gives the total
+#pragma unroll
+                                for (int c = 0; c < NDC; ++c) dW[c] = (R)0;
+                                if (row_valid) {
+                                    for (int m = rl; m < NCL; m += lpr) {
+#pragma unroll
+                                        for (int c = 0; c < NDC; ++c) dW[c] += gath[(size_t)m * NVP + row * NDC + c];
+                                    }
+                                }
                                 __syncwarp();
                                 row_butterfly<R, NDC>(dW, lpr);
                             }
@@ -541,26 +723,25 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     } else {
                         total = totbuf;  // one cluster, one GPU: the cluster partial is the total
                     }
+                    if (prof) tick(6);  // leader: cluster sum + hops N / B (thread 0 is a row lane)
                     __syncthreads();  // total complete
                     // hop C: the total -> every member's totbuf
-                    if (tid >= 1 && tid < CS) {
-                        cl_fence_async();
-                        cl_bulk_copy(cl_mapa(cl_smem_u32(totbuf), (uint32_t)tid), cl_smem_u32(total), NVB, cl_mapa(mb_tot, (uint32_t)tid));
+                    for (int q = tid; q < (CS - 1) * NCH; q += BLOCK) {
+                        const uint32_t r = 1u + (uint32_t)(q / NCH), j = (uint32_t)(q % NCH);
+                        const uint4 v = reinterpret_cast<const uint4*>(total)[j];
+                        cl_st_async16(cl_mapa(cl_smem_u32(totbuf) + 16u * j, r), v, cl_mapa(mb_tot, r));
                     }
                 }
                 if (!leader) total = totbuf;
             }
             for (int j = tid; j < NV; j += BLOCK) Wsm[(j / AW) * WS + j % AW] += total[j];
-            if (prof) { c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
+            }
+            if (prof) tick(3);
             __syncthreads();
-            if (prof) { c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
+            if (prof) tick(4);
         }
     }
 
-    if (prof) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a.phase_prof[b * 8 + q] += pc[q];
-    }
     if (resident && active) {
         a.ep_steps[i] = ep;
         a.actions[i] = act;
@@ -577,6 +758,9 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     }
     if (SHAREDW && b == 0) {
         for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[(j / AW) * WS + j % AW];
+        if (FX) {  // every CTA holds the same running sums (multi-GPU: only CTA 0 tracks the local table)
+            for (int j = tid; j < 4 * NV; j += BLOCK) sy.prev[j] = prevs[(j / NV) * NVP8 + j % NV];
+        }
     }
     if (SHAREDW && CS > 1) cl_sync();  // nobody leaves while a bulk copy may still read or write its shared memory
 }

@@ -126,10 +126,10 @@ class Engine:
 
     def launch_shape(self):
         """rsrl_engine_get_launch_shape as a dict (the fp32 summation order is a function of it: oracle/oracle32.cpp)."""
-        out = np.zeros(16, dtype=np.int32)
+        out = np.zeros(24, dtype=np.int32)
         check(self.lib.rsrl_engine_get_launch_shape(self.h, ip(out)))
         keys = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "lpg", "seg_len", "pe_smem", "world",
-                "rank", "peers", "smem", "tile", "f4"]
+                "rank", "peers", "smem", "tile", "f4", "fx"]
         return dict(zip(keys, (int(v) for v in out)))
 
     def set_epsilon(self, eps):

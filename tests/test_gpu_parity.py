@@ -309,7 +309,7 @@ def test_engine_f32_teacher_forced(E, oracle, name, kw):
     """Each step starts from the same inputs on both sides (oracle state/weights copied from the device):
     next states within 1e-12 (f64 physics), TD errors within 1.2e-5 relative to the largest |TD error| / |weight|, weights within 1e-6 relative (fp32 features/Q),
     actions identical wherever the oracle's decision margin exceeds the fp32 resolution of Q."""
-    cfg = _mc_cfg(dtype=abi.F32, n_envs=512, **kw)
+    cfg = _mc_cfg(dtype=abi.F32, n_envs=512, update_scale=abi.SCALE_MEAN, **kw)   # MEAN: lr * 512 envs summed would diverge within a few steps
     rng = np.random.default_rng(4)
     with E.Engine(cfg) as e:
         o = oracle.Engine(cfg)

@@ -47,6 +47,12 @@ def _exact(e, o, what=""):
 # ---------------------------------------------------------------------------------------------
 # the elementary functions and the physics: same bits on both sides
 # ---------------------------------------------------------------------------------------------
+def _same_bits(a, b):
+    """identical bit patterns; NaNs only have to be NaN on both sides (x86 and the GPU differ in the default NaN's sign bit)"""
+    nan = np.isnan(a)
+    return (nan == np.isnan(b)).all() and (a[~nan].view(np.uint64) == b[~nan].view(np.uint64)).all()
+
+
 def test_math_functions_bit_exact(E, oracle32):
     rng = np.random.default_rng(0)
     xs64 = np.concatenate([rng.uniform(-40, 40, 200000), rng.uniform(-4, 4, 200000), rng.uniform(-1e6, 1e6, 50000),
@@ -54,16 +60,16 @@ def test_math_functions_bit_exact(E, oracle32):
     for fn in (0, 1):
         a, b = E.math_probe(fn, xs64), oracle32.math(fn, xs64)
         inside = np.abs(xs64) < 1048576.0     # beyond: the platform libm on each side (documented, never reached by the domains)
-        assert (a[inside].view(np.uint64) == b[inside].view(np.uint64)).all(), f"fn {fn}"
+        assert _same_bits(a[inside], b[inside]), f"fn {fn}"
     xs32 = np.concatenate([rng.uniform(0, 1, 300000), rng.uniform(-8, 8, 100000), rng.uniform(-1e7, 1e7, 1000),
                            [0.0, 0.25, 0.5, 0.75, 1.0, 1e10, np.inf, np.nan]]).astype(np.float32).astype(np.float64)
     for fn in (2, 3):
         a, b = E.math_probe(fn, xs32), oracle32.math(fn, xs32)
-        assert (a.view(np.uint64) == b.view(np.uint64)).all(), f"fn {fn}"
+        assert _same_bits(a, b), f"fn {fn}"
     xe = np.concatenate([rng.uniform(-110, 90, 300000), rng.uniform(-5, 5, 100000), [0.0, 88.7228, 88.8, -103.9, -104.0, np.inf, -np.inf, np.nan]])
     xe = xe.astype(np.float32).astype(np.float64)
     a, b = E.math_probe(4, xe), oracle32.math(4, xe)
-    assert (a.view(np.uint64) == b.view(np.uint64)).all()
+    assert _same_bits(a, b)
 
 
 @pytest.mark.parametrize("domain", [MC, CP, AC])
@@ -80,7 +86,7 @@ def test_domain_step_bit_exact(E, oracle32, oracle, domain):
         assert (ns.view(np.uint64) == ns2.view(np.uint64)).all() and (r == r2).all() and (t == t2).all()
         # and within a few ulp of the libm-based f64 oracle (the reference's arithmetic)
         ns3, r3, t3 = oracle.domain_step(domain, s, a)
-        assert np.abs(ns - ns3).max() < 1e-13 and (t == t3).mean() > 0.9999
+        assert (np.abs(ns - ns3) / np.maximum(1.0, np.abs(ns3))).max() < (1e-12 if domain == AC else 2e-14) and (t == t3).mean() > 0.9999
         s = ns
 
 
@@ -112,6 +118,7 @@ def test_cfg2_full_size_teacher_forced_vs_f64_oracle(E, oracle):
         o = oracle.Engine(cfg)
         e.set_weights(rng.normal(size=(36, 3)) * 0.5)
         e.step(3)
+        o.step(3)   # same batched-step index on both sides: it is the RNG draw counter
         for t in range(20):
             o.set_states(e.states())
             o.set_weights(e.weights())
@@ -230,6 +237,7 @@ def test_cfg5_shard_teacher_forced_vs_f64_oracle(E, oracle, name, kw):
         o = oracle.Engine(cfg)
         e.set_weights(rng.normal(size=(36, aw)) * 0.3)
         e.step(4)
+        o.step(4)   # same batched-step index on both sides: it is the RNG draw counter
         for t in range(8):
             o.set_states(e.states())
             o.set_weights(e.weights())
