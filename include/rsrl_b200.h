@@ -57,7 +57,11 @@ typedef enum rsrl_status {
 } rsrl_status_t;
 
 /* rsrl_domains/src/{mountain_car/discrete.rs, cart_pole.rs, acrobot.rs} */
-typedef enum rsrl_domain { RSRL_MOUNTAIN_CAR = 0, RSRL_CART_POLE = 1, RSRL_ACROBOT = 2 } rsrl_domain_t;
+typedef enum rsrl_domain {
+    RSRL_MOUNTAIN_CAR = 0, RSRL_CART_POLE = 1, RSRL_ACROBOT = 2,
+    /* component-level only (rsrl_domain_ex_*): rsrl_domains/src/mountain_car/continuous.rs, rsrl_domains/src/hiv.rs */
+    RSRL_CONTINUOUS_MOUNTAIN_CAR = 3, RSRL_HIV = 4
+} rsrl_domain_t;
 /* lfa::basis::{Fourier, Polynomial, TileCoding} (+ .with_bias()) */
 typedef enum rsrl_basis { RSRL_FOURIER = 0, RSRL_POLYNOMIAL = 1, RSRL_TILE_CODING = 2 } rsrl_basis_t;
 /* rsrl/src/control/td/{q_learning,sarsa,expected_sarsa,sarsa_lambda,q_lambda,pal}.rs, rsrl/src/prediction/td/{td,td_lambda}.rs */
@@ -230,6 +234,16 @@ int rsrl_domain_step(int32_t domain, int64_t n, double* states_inout, const int3
                      double* rewards_out, uint8_t* terminal_out);
 /* Domain::emit(): Observation::Terminal? */
 int rsrl_domain_is_terminal(int32_t domain, int64_t n, const double* states, uint8_t* terminal_out);
+/* ---- the other ODE / continuous-action domains, as batched Domain::step / Domain::emit (the engine does not drive them) ----
+ * ContinuousMountainCar (D = 2, n_actions reported as 0: the action is a double, clipped onto [-1, 1] like Interval::map_onto,
+ * continuous.rs:41-48) and HIVTreatment (D = 6 raw state T1, T1S, T2, T2S, V, E; 4 actions = ALL_ACTIONS hiv.rs:35; 1000 RK4
+ * sub-steps per step :58-69; observation = clip(-5, log10(state), 8) :131-135; reward from the observation :141-148).
+ * `actions` (int32) is read by HIV, `actions_continuous` (f64) by ContinuousMountainCar; obs_out may be NULL. */
+int rsrl_domain_ex_info(int32_t domain, int32_t* dim, int32_t* n_actions, double* lo /* D */, double* hi, double* start);
+int rsrl_domain_ex_step(int32_t domain, int64_t n, double* states_inout, const int32_t* actions, const double* actions_continuous,
+                        double* obs_out, double* rewards_out, uint8_t* terminal_out);
+int rsrl_domain_ex_emit(int32_t domain, int64_t n, const double* states, double* obs_out, uint8_t* terminal_out);
+const char* rsrl_domain_ex_last_error(void);
 /* Basis::project: features_out N x F f64 (dense; TileCoding writes 1.0 at active rows) */
 int rsrl_basis_project(const rsrl_config_t* cfg, int64_t n, const double* states, double* features_out);
 /* LFA::evaluate: q_out N x A = phi(s)^T W, W is F x A */

@@ -41,6 +41,10 @@ def lib():
             "orc_domain_default": (None, [C.c_int, _dp]),
             "orc_domain_is_terminal": (C.c_int, [C.c_int, _dp]),
             "orc_domain_step": (None, [C.c_int, _dp, C.c_int, _dp, _ip]),
+            "orc_domain_ex_dim": (C.c_int, [C.c_int]),
+            "orc_domain_ex_default": (None, [C.c_int, _dp]),
+            "orc_domain_ex_emit": (None, [C.c_int, _dp, _dp, _ip]),
+            "orc_domain_ex_step": (None, [C.c_int, _dp, C.c_double, _dp, _dp, _ip]),
             "orc_basis_n_features": (C.c_int64, [_cfgp]),
             "orc_fourier_coefficients": (None, [C.c_int, C.c_int, _dp]),
             "orc_basis_project": (None, [_cfgp, _dp, _dp]),
@@ -65,6 +69,9 @@ def lib():
             "orc_engine_get_episode_steps": (None, [C.c_void_p, _ip]),
             "orc_engine_get_weights": (None, [C.c_void_p, _dp]),
             "orc_engine_set_weights": (None, [C.c_void_p, _dp]),
+            "orc_engine_get_aux_weights": (None, [C.c_void_p, _dp]),
+            "orc_engine_set_aux_weights": (None, [C.c_void_p, _dp]),
+            "orc_engine_rollout": (C.c_int64, [C.c_void_p, C.c_int64, _dp, C.c_int64, C.c_int, C.c_uint64, _dp, _dp, _ip, _dp, _u8p]),
             "orc_engine_get_traces": (None, [C.c_void_p, _dp]),
             "orc_engine_set_traces": (None, [C.c_void_p, _dp]),
             "orc_engine_get_td_errors": (None, [C.c_void_p, _dp]),
@@ -131,6 +138,36 @@ def domain_step(domain, states, actions):
         lib().orc_domain_step(domain, _d(row), int(actions[i]), C.byref(r), C.byref(t))
         rewards[i], terminal[i] = r.value, t.value
     return ns, rewards, terminal.astype(np.uint8)
+
+
+def domain_ex_default(domain):
+    s = np.zeros(lib().orc_domain_ex_dim(domain))
+    lib().orc_domain_ex_default(domain, _d(s))
+    return s
+
+
+def domain_ex_emit(domain, states):
+    D = lib().orc_domain_ex_dim(domain)
+    s = f64(states).reshape(-1, D)
+    obs, term = np.zeros_like(s), np.zeros(s.shape[0], dtype=np.int32)
+    t = C.c_int32()
+    for i in range(s.shape[0]):
+        lib().orc_domain_ex_emit(domain, _d(s[i]), _d(obs[i]), C.byref(t))
+        term[i] = t.value
+    return obs, term.astype(np.uint8)
+
+
+def domain_ex_step(domain, states, actions):
+    """Domain::step of ContinuousMountainCar (actions: forces) / HIVTreatment (actions: indices). Returns (states, obs, rewards, terminal)."""
+    D = lib().orc_domain_ex_dim(domain)
+    ns = f64(states).reshape(-1, D).copy()
+    n = ns.shape[0]
+    obs, rewards, term = np.zeros_like(ns), np.zeros(n), np.zeros(n, dtype=np.uint8)
+    r, t = C.c_double(), C.c_int32()
+    for i in range(n):
+        lib().orc_domain_ex_step(domain, _d(ns[i]), float(actions[i]), _d(obs[i]), C.byref(r), C.byref(t))
+        rewards[i], term[i] = r.value, t.value
+    return ns, obs, rewards, term
 
 
 def n_features(cfg):
@@ -299,6 +336,29 @@ class Engine:
         w = f64(w)
         assert w.shape == self._wshape()
         lib().orc_engine_set_weights(self.h, _d(w))
+
+    def aux_weights(self):
+        out = np.empty(self._wshape())
+        lib().orc_engine_get_aux_weights(self.h, _d(out))
+        return out
+
+    def set_aux_weights(self, w):
+        w = f64(w)
+        assert w.shape == self._wshape()
+        lib().orc_engine_set_aux_weights(self.h, _d(w))
+
+    def rollout(self, n=None, init_states=None, step_limit=500, greedy=True, draw=0):
+        """Domain::rollout per env (rsrl_domains/src/lib.rs:448-479); same dict layout as rsrl_b200.engine.Engine.rollout"""
+        n = self.N if n is None else n
+        T = max(step_limit - 1, 1)
+        out = dict(start=np.zeros((n, self.D)), next=np.zeros((n, T, self.D)), actions=np.full((n, T), -1, dtype=np.int32),
+                   rewards=np.zeros((n, T)), terminal=np.zeros((n, T), dtype=np.uint8), len=np.zeros(n, dtype=np.int32))
+        init = None if init_states is None else f64(init_states)
+        for i in range(n):
+            st, nx, ac, rw, tm = out["start"][i], out["next"][i], out["actions"][i], out["rewards"][i], out["terminal"][i]
+            out["len"][i] = lib().orc_engine_rollout(self.h, i, None if init is None else _d(init[i]), step_limit, 1 if greedy else 0,
+                                                     draw, _d(st), _d(nx), _i(ac), _d(rw), tm.ctypes.data_as(_u8p))
+        return out
 
     def traces(self):
         out = np.zeros((self.N, self.F, self.AW))

@@ -156,6 +156,80 @@ static void ac_step(double* s, int action, double* reward, int* terminal) {
     *reward = *terminal ? 0.0 : -1.0; /* :32-33,134-138 */
 }
 
+/* ------------------------------------------------------------------------- */
+/* rsrl_domains/src/mountain_car/continuous.rs:8-85 and rsrl_domains/src/hiv.rs:6-153 (component level) */
+/* ------------------------------------------------------------------------- */
+int orc_domain_ex_dim(int domain) { return domain == RSRL_HIV ? 6 : 2; }
+
+void orc_domain_ex_default(int domain, double* s) {
+    if (domain == RSRL_HIV) { /* hiv.rs:105-109 */
+        const double d[6] = {163573.0, 11945.0, 5.0, 46.0, 63919.0, 24.0};
+        memcpy(s, d, sizeof d);
+    } else { s[0] = -0.5; s[1] = 0.0; } /* continuous.rs:51-53 */
+}
+
+static void hiv_grad(const double* eps, const double* b, double* out) { /* hiv.rs:72-103 */
+    const double LAMBDA1 = 1e4, LAMBDA2 = 31.98, D1 = 0.01, D2 = 0.01, F = 0.34, K1 = 8e-7, K2 = 1e-4, DELTA = 0.7, M1 = 1e-5, M2 = 1e-5,
+                 NT = 100.0, C = 13.0, RHO1 = 1.0, RHO2 = 1.0, LAMBDA_E = 1.0, BE = 0.3, KB = 100.0, DE = 0.25, KD = 500.0, DELTA_E = 0.1;
+    double t1 = b[0], t1s = b[1], t2 = b[2], t2s = b[3], v = b[4], e = b[5];
+    double tmp1 = (1.0 - eps[0]) * K1 * v * t1;
+    double tmp2 = (1.0 - F * eps[0]) * K2 * v * t2;
+    double sum_ts = t1s + t2s;
+    out[0] = LAMBDA1 - D1 * t1 - tmp1;
+    out[1] = tmp1 - DELTA * t1s - M1 * e * t1s;
+    out[2] = LAMBDA2 - D2 * t2 - tmp2;
+    out[3] = tmp2 - DELTA * t2s - M2 * e * t2s;
+    out[4] = (1.0 - eps[1]) * NT * DELTA * sum_ts - C * v - ((1.0 - eps[0]) * RHO1 * K1 * t1 + (1.0 - F * eps[0]) * RHO2 * K2 * t2) * v;
+    out[5] = LAMBDA_E + BE * sum_ts / (sum_ts + KB) * e - DE * sum_ts / (sum_ts + KD) * e - DELTA_E * e;
+}
+
+void orc_domain_ex_emit(int domain, const double* s, double* obs, int* terminal) {
+    if (domain == RSRL_HIV) { /* hiv.rs:131-135 */
+        for (int d = 0; d < 6; ++d) obs[d] = clip(-5.0, log10(s[d]), 8.0);
+        *terminal = 0;
+    } else { /* continuous.rs:60-66 */
+        obs[0] = s[0]; obs[1] = s[1];
+        *terminal = s[0] >= 0.6;
+    }
+}
+
+/* Domain::step: `action` is the index for HIV and the force for ContinuousMountainCar */
+void orc_domain_ex_step(int domain, double* s, double action, double* obs, double* reward, int* terminal) {
+    if (domain == RSRL_HIV) {
+        static const double ALL[4][2] = {{0.0, 0.0}, {0.7, 0.0}, {0.0, 0.3}, {0.7, 0.3}}; /* hiv.rs:35 */
+        const double* eps = ALL[(int)action];
+        const double dt = 5.0 / (double)1000; /* DT_STEP :31 */
+        double y[6];
+        memcpy(y, s, sizeof y);
+        for (int it = 0; it < 1000; ++it) { /* :61-64, runge_kutta4 of ode.rs:1-43 on 6 components */
+            double k1[6], k2[6], k3[6], k4[6], tmp[6];
+            int i;
+            hiv_grad(eps, y, k1);
+            for (i = 0; i < 6; ++i) k1[i] = k1[i] * dt;
+            for (i = 0; i < 6; ++i) tmp[i] = y[i] + k1[i] / 2.0;
+            hiv_grad(eps, tmp, k2);
+            for (i = 0; i < 6; ++i) k2[i] = k2[i] * dt;
+            for (i = 0; i < 6; ++i) tmp[i] = y[i] + k2[i] / 2.0;
+            hiv_grad(eps, tmp, k3);
+            for (i = 0; i < 6; ++i) k3[i] = k3[i] * dt;
+            for (i = 0; i < 6; ++i) tmp[i] = y[i] + k3[i];
+            hiv_grad(eps, tmp, k4);
+            for (i = 0; i < 6; ++i) k4[i] = k4[i] * dt;
+            for (i = 0; i < 6; ++i) y[i] += (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0;
+        }
+        memcpy(s, y, sizeof y);
+        orc_domain_ex_emit(domain, s, obs, terminal);
+        *reward = (1e3 * obs[5] - 0.1 * obs[4] - 2e4 * (eps[0] * eps[0]) - 2e3 * (eps[1] * eps[1])) / 1e5; /* :141-148 */
+    } else { /* continuous.rs:41-48,68-79; Interval::map_onto clips onto [-1, 1] */
+        double a = clip(-1.0, action, 1.0);
+        double dv = 0.0015 * a + MC_FORCE_G * cos(MC_HILL_FREQ * s[0]);
+        s[1] = clip(MC_V_MIN, s[1] + dv, MC_V_MAX);
+        s[0] = clip(MC_X_MIN, s[0] + s[1], MC_X_MAX);
+        orc_domain_ex_emit(domain, s, obs, terminal);
+        *reward = *terminal ? 0.0 : -1.0;
+    }
+}
+
 /* ---- Domain trait dispatch (rsrl_domains/src/lib.rs:417-446) ---- */
 int orc_domain_dim(int domain) { return domain == RSRL_MOUNTAIN_CAR ? 2 : 4; }
 int orc_domain_n_actions(int domain) { return domain == RSRL_CART_POLE ? 2 : 3; }
@@ -606,13 +680,13 @@ static double a2c_handle(orc_engine_t* e, int64_t g, uint64_t draw, const double
     }
     double* phi = project_alloc(c, from);
     const double cq = (c->lr * residual) / e->step_scale;
-    accumulate_col(e, dst, a, cq, phi);              /* sarsa.rs:67-73 -> SGD */
-    /* critic closure (a2c.rs:40-45) on the updated Q: only column a of Q(s) changed */
+    /* critic closure (a2c.rs:40-45) on the updated Q: only column a of Q(s) changed (W may alias dst: read it before the update lands) */
     {
         double acc = 0.0;
         for (int64_t k = 0; k < F; ++k) acc = acc + phi[k] * (W[k * A + a] + cq * phi[k]);
         qs[a] = acc;
     }
+    accumulate_col(e, dst, a, cq, phi);              /* sarsa.rs:67-73 -> SGD */
     double ps[16], ev = 0.0;
     gibbs_probs(c, W2, A, from, ps);
     for (int j = 0; j < A; ++j) ev = ev + qs[j] * ps[j];
@@ -846,8 +920,7 @@ int64_t orc_engine_rollout(orc_engine_t* e, int64_t i, const double* init_state,
     const double* Wq = c->weight_mode == RSRL_PER_ENV ? e->W + i * e->F * e->AW : e->W;
     const double* Wp = c->algo == RSRL_A2C ? (c->weight_mode == RSRL_PER_ENV ? e->W2 + i * e->F * e->AW : e->W2) : Wq;
     const int policy = c->algo == RSRL_A2C ? RSRL_SOFTMAX : c->policy;
-    const int64_t tmax = step_limit > 0 ? (step_limit - 1 > 1 ? step_limit - 1 : 1) : -1;
-    const int64_t take = step_limit > 0 ? (step_limit - 1 > 0 ? step_limit - 1 : 0) : -1; /* iter.take(sl.saturating_sub(1)) */
+    const int64_t take = step_limit - 1 > 0 ? step_limit - 1 : 0; /* iter.take(sl.saturating_sub(1)), lib.rs:472-476 */
     double s[RSRL_MAX_DIM];
     int64_t n = 0;
     int terminated = 0;
@@ -855,8 +928,7 @@ int64_t orc_engine_rollout(orc_engine_t* e, int64_t i, const double* init_state,
     else fresh_state(e, g, (int64_t)draw, s);
     memcpy(start_out, s, (size_t)e->D * sizeof(double)); /* let start = self.emit() */
     for (int64_t j = 0;; ++j) {
-        if (j > 0 && terminated) break;                 /* successors: Observation::Terminal => None */
-        if (take >= 0 && j >= take && !(j == 0)) break; /* .take(sl - 1): the first step below is executed even when it is not recorded */
+        if (j > 0 && (terminated || j >= take)) break;  /* successors: Observation::Terminal => None; .take(sl - 1) */
         double* q = evaluate_alloc(c, Wp, e->AW, s);
         int a, nf = 0;
         if (greedy) {
@@ -869,12 +941,11 @@ int64_t orc_engine_rollout(orc_engine_t* e, int64_t i, const double* init_state,
         }
         free(q);
         double r;
-        orc_domain_step(c->domain, s, a, &r, &terminated);
-        if (take >= 0 && j >= take) break;              /* step_limit == 1: executed, not recorded (lib.rs:472-476) */
+        orc_domain_step(c->domain, s, a, &r, &terminated);   /* the first step is executed even when nothing is recorded (lib.rs:460-462) */
+        if (j >= take) break;
         memcpy(next_out + j * e->D, s, (size_t)e->D * sizeof(double));
         actions_out[j] = a; rewards_out[j] = r; terminal_out[j] = (uint8_t)terminated;
         n = j + 1;
-        if (tmax >= 0 && n >= tmax && take >= 0 && n >= take) break;
     }
     return n;
 }

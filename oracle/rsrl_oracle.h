@@ -35,6 +35,12 @@ void orc_domain_default(int domain, double* s);               /* Default::defaul
 int  orc_domain_is_terminal(int domain, const double* s);     /* emit() is Observation::Terminal */
 void orc_domain_step(int domain, double* s, int action, double* reward, int* terminal); /* Domain::step */
 
+/* ContinuousMountainCar (continuous.rs) / HIVTreatment (hiv.rs): raw state in, observation out */
+int  orc_domain_ex_dim(int domain);
+void orc_domain_ex_default(int domain, double* s);
+void orc_domain_ex_emit(int domain, const double* s, double* obs, int* terminal);
+void orc_domain_ex_step(int domain, double* s, double action, double* obs, double* reward, int* terminal);
+
 /* ---- bases (lfa crate, restated from its published algorithm) ---- */
 int64_t orc_basis_n_features(const rsrl_config_t* cfg);
 void orc_fourier_coefficients(int order, int dim, double* coef /* (F-1) x dim */);

@@ -10,9 +10,9 @@ LIB_PATH = os.path.join(HERE, "csrc", "librsrl_b200.so")
 
 # enums (include/rsrl_b200.h)
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ENONFINITE, ECOMM, ENODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
-MOUNTAIN_CAR, CART_POLE, ACROBOT = 0, 1, 2
+MOUNTAIN_CAR, CART_POLE, ACROBOT, CONTINUOUS_MOUNTAIN_CAR, HIV = 0, 1, 2, 3, 4
 FOURIER, POLYNOMIAL, TILE_CODING = 0, 1, 2
-QLEARNING, SARSA, EXPECTED_SARSA, SARSA_LAMBDA, Q_LAMBDA, TD_LAMBDA, TD0, PAL = range(8)
+QLEARNING, SARSA, EXPECTED_SARSA, SARSA_LAMBDA, Q_LAMBDA, TD_LAMBDA, TD0, PAL, GREEDY_GQ, A2C = range(10)
 GREEDY, EPSILON_GREEDY, RANDOM, SOFTMAX = 0, 1, 2, 3
 TRACE_ACCUMULATE, TRACE_REPLACE, TRACE_DUTCH = 0, 1, 2
 SHARED, PER_ENV = 0, 1
@@ -106,6 +106,9 @@ SYMBOLS = {
     "rsrl_engine_get_episode_steps": (C.c_int, [_eng, _ip]),
     "rsrl_engine_get_weights": (C.c_int, [_eng, _dp]),
     "rsrl_engine_set_weights": (C.c_int, [_eng, _dp]),
+    "rsrl_engine_get_aux_weights": (C.c_int, [_eng, _dp]),
+    "rsrl_engine_set_aux_weights": (C.c_int, [_eng, _dp]),
+    "rsrl_engine_rollout": (C.c_int, [_eng, C.c_int64, _dp, C.c_int64, C.c_int32, C.c_uint64, _dp, _dp, _ip, _dp, _u8p, _ip]),
     "rsrl_engine_get_traces": (C.c_int, [_eng, _dp]),
     "rsrl_engine_set_traces": (C.c_int, [_eng, _dp]),
     "rsrl_engine_get_td_errors": (C.c_int, [_eng, _dp]),
@@ -125,6 +128,10 @@ SYMBOLS = {
     "rsrl_domain_info": (C.c_int, [C.c_int32, _ip, _ip, _dp, _dp, _dp]),
     "rsrl_domain_step": (C.c_int, [C.c_int32, C.c_int64, _dp, _ip, _dp, _u8p]),
     "rsrl_domain_is_terminal": (C.c_int, [C.c_int32, C.c_int64, _dp, _u8p]),
+    "rsrl_domain_ex_info": (C.c_int, [C.c_int32, _ip, _ip, _dp, _dp, _dp]),
+    "rsrl_domain_ex_step": (C.c_int, [C.c_int32, C.c_int64, _dp, _ip, _dp, _dp, _dp, _u8p]),
+    "rsrl_domain_ex_emit": (C.c_int, [C.c_int32, C.c_int64, _dp, _dp, _u8p]),
+    "rsrl_domain_ex_last_error": (C.c_char_p, []),
     "rsrl_basis_project": (C.c_int, [_cfgp, C.c_int64, _dp, _dp]),
     "rsrl_lfa_evaluate": (C.c_int, [_cfgp, C.c_int64, _dp, _dp, _dp]),
     "rsrl_lfa_update_index": (C.c_int, [_cfgp, C.c_int64, _dp, _ip, _dp, _dp]),

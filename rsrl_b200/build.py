@@ -17,14 +17,14 @@ HEADERS = ["hostdev.h", "device.cuh", "core.cuh", "kernels.cuh", "persistent.cuh
 
 
 # headers only some translation units include (kept out of HEADERS so that editing them does not rebuild everything)
-EXTRA_DEPS = {"abi.cu": ["f4tc_launch.h"], "f4tc_inst.cu": ["f4tc_launch.h", "f4tc.cuh"]}
+EXTRA_DEPS = {"abi.cu": ["f4tc_launch.h", "twotable.cuh"], "inst.cu": ["twotable.cuh"], "f4tc_inst.cu": ["f4tc_launch.h", "f4tc.cuh"]}
 
 
 def _units():
     # RSRL_BUILD_DOMAINS=0 (development only) leaves the CartPole / Acrobot instantiations out for fast iteration;
     # the default builds everything.
     doms = {int(d) for d in os.environ.get("RSRL_BUILD_DOMAINS", "0,1,2").split(",")}
-    units = [("abi.o", "abi.cu", NOFMAD), ("f4tc.o", "f4tc_inst.cu", [])]
+    units = [("abi.o", "abi.cu", NOFMAD), ("f4tc.o", "f4tc_inst.cu", []), ("domains_ex.o", "domains_ex.cu", NOFMAD)]
     for rname, rtype in (("f32", "float"), ("f64", "double")):
         units.append((f"tile_{rname}.o", "tile_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))
         units.append((f"f4_{rname}.o", "f4_inst.cu", [f"-DRSRL_REAL={rtype}", f"-DRSRL_SUFFIX={rname}"]))

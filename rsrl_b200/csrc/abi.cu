@@ -58,6 +58,7 @@ struct DevBuf {  // RAII device allocation for the stateless entry points
 static int dom_dim(int d) { return d == RSRL_MOUNTAIN_CAR ? 2 : 4; }
 static int dom_actions(int d) { return d == RSRL_CART_POLE ? 2 : 3; }
 static bool algo_td_pred(int a) { return a == RSRL_TD_LAMBDA || a == RSRL_TD0; }
+static bool algo_two_tables(int a) { return a == RSRL_GREEDY_GQ || a == RSRL_A2C; }
 static int64_t ipow(int64_t b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
 
 static int validate(const rsrl_config_t* c) {
@@ -65,7 +66,7 @@ static int validate(const rsrl_config_t* c) {
     if (c->struct_size != sizeof(rsrl_config_t)) return fail(RSRL_EINVAL, "rsrl_config_t.struct_size mismatch (ABI)");
     if (c->domain < 0 || c->domain > 2) return fail(RSRL_EINVAL, "unknown domain");
     if (c->basis < 0 || c->basis > 2) return fail(RSRL_EINVAL, "unknown basis");
-    if (c->algo < 0 || c->algo > RSRL_PAL) return fail(RSRL_EINVAL, "unknown algo");
+    if (c->algo < 0 || c->algo > RSRL_A2C) return fail(RSRL_EINVAL, "unknown algo");
     if (c->policy < 0 || c->policy > RSRL_SOFTMAX) return fail(RSRL_EINVAL, "unknown policy");
     if (c->dtype != RSRL_F32 && c->dtype != RSRL_F64) return fail(RSRL_EINVAL, "unknown dtype");
     if (c->weight_mode != RSRL_SHARED && c->weight_mode != RSRL_PER_ENV) return fail(RSRL_EINVAL, "unknown weight_mode");
@@ -88,6 +89,8 @@ static int validate(const rsrl_config_t* c) {
         if (c->tiles_per_dim < 1) return fail(RSRL_EINVAL, "tiles_per_dim must be >= 1");
         if (c->memory_size < 2 || (c->memory_size & (c->memory_size - 1))) return fail(RSRL_EINVAL, "memory_size must be a power of two");
     }
+    if (c->algo == RSRL_A2C && c->policy != RSRL_SOFTMAX)
+        return fail(RSRL_EINVAL, "A2C: the policy is the Gibbs / Softmax policy over its own LFA (examples/a2c.rs:28): set policy = RSRL_SOFTMAX, tau in epsilon");
     if (algo_td_pred(c->algo) && c->policy != RSRL_RANDOM)
         return fail(RSRL_EINVAL, "TD(0)/TD(lambda) predict V(s): the behaviour policy must be RSRL_RANDOM");
     return RSRL_OK;
@@ -130,6 +133,17 @@ static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStrea
     static const eval_launch_fn table[2][3] = {{launch_eval_f32_d0, launch_eval_f32_d1, launch_eval_f32_d2},
                                                {launch_eval_f64_d0, launch_eval_f64_d1, launch_eval_f64_d2}};
     return table[k.dtype][k.domain](k, e, st);
+}
+
+static cudaError_t dispatch_two(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    static const two_launch_fn table[2][3] = {{launch_two_f32_d0, launch_two_f32_d1, launch_two_f32_d2},
+                                              {launch_two_f64_d0, launch_two_f64_d1, launch_two_f64_d2}};
+    return table[k.dtype][k.domain](k, mode, ext, a, grid, block, smem, st);
+}
+static cudaError_t dispatch_rollout(const BasisKey& k, const RolloutArgs& ra, cudaStream_t st) {
+    static const rollout_launch_fn table[2][3] = {{launch_rollout_f32_d0, launch_rollout_f32_d1, launch_rollout_f32_d2},
+                                                  {launch_rollout_f64_d0, launch_rollout_f64_d1, launch_rollout_f64_d2}};
+    return table[k.dtype][k.domain](k, ra, st);
 }
 
 static cudaError_t dispatch_persist(const BasisKey& k, int mode, const StepArgs& a, int k_steps, const SyncArgs& sy, const PeerArgs& pe, int grid, int block, size_t smem, cudaStream_t st, int* max_clusters = nullptr) {
@@ -180,6 +194,7 @@ struct rsrl_engine {
     rsrl_config_t cfg;
     BasisKey key;
     int D = 0, A = 0, AW = 0;
+    int WT = 1;  // weight tables: 2 for GreedyGQ (fa_q, fa_td) and A2C (critic Q, policy LFA); table t starts at t * FA (* N for PER_ENV)
     int64_t N = 0, NG = 0, F = 0, FA = 0;
     bool has_trace = false;
     size_t rsz = 4;
@@ -231,7 +246,7 @@ struct rsrl_engine {
     bool peers_attached = false;
 };
 
-static size_t wcount(const rsrl_engine* e) { return (size_t)e->FA * (e->cfg.weight_mode == RSRL_PER_ENV ? (size_t)e->N : 1); }
+static size_t wcount(const rsrl_engine* e) { return (size_t)e->FA * (e->cfg.weight_mode == RSRL_PER_ENV ? (size_t)e->N : 1); }  // one table
 
 static int ensure_stage(rsrl_engine* e, size_t elems) {
     if (elems <= e->stage_elems) return RSRL_OK;
@@ -245,6 +260,13 @@ static int ensure_stage(rsrl_engine* e, size_t elems) {
 static void choose_launch(rsrl_engine* e) {
     if (e->cfg.weight_mode == RSRL_PER_ENV) {
         e->block = 128; e->smem = 0;
+    } else if (e->WT == 2) {  // twotable.cuh: W[2][FA] + phi(s) and phi(s') rows + three coefficient planes
+        int block = 256;
+        for (;; block /= 2) {
+            e->smem = ((((size_t)2 * e->FA + 3) & ~(size_t)3) + (size_t)2 * e->F * (block + 1) + (size_t)3 * e->AW * block) * e->rsz;
+            if (e->smem <= 200 * 1024 || block == 32) break;
+        }
+        e->block = block;
     } else {
         const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;
         int block = 256;
@@ -303,6 +325,7 @@ static void choose_persistent(rsrl_engine* e) {
     e->persistent = false;
     e->pmode = e->cfg.weight_mode;
     if (e->has_trace && e->cfg.weight_mode == RSRL_PER_ENV) return;  // per-env W + traces: per-step kernels
+    if (e->WT == 2) return;                                           // GreedyGQ / A2C: per-step kernels (twotable.cuh)
     int dev = e->cfg.device, sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) return;
@@ -374,15 +397,17 @@ static StepArgs make_args(rsrl_engine* e) {
 
 template <typename R>
 static cudaError_t launch_reduce(rsrl_engine* e, int n_blocks, bool to_dw) {
-    const int threads = 128, blocks = (int)((e->FA + threads - 1) / threads);
-    reduce_partials_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<const R*>(e->partials), n_blocks, (int)e->FA,
+    const int fa = (int)e->FA * e->WT;
+    const int threads = 128, blocks = (fa + threads - 1) / threads;
+    reduce_partials_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<const R*>(e->partials), n_blocks, fa,
                                                                   static_cast<R*>(e->W), to_dw ? static_cast<R*>(e->dW) : nullptr);
     return cudaGetLastError();
 }
 template <typename R>
 static cudaError_t launch_add(rsrl_engine* e) {
-    const int threads = 128, blocks = (int)((e->FA + threads - 1) / threads);
-    add_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<R*>(e->W), static_cast<const R*>(e->dW), (int)e->FA);
+    const int fa = (int)e->FA * e->WT;
+    const int threads = 128, blocks = (fa + threads - 1) / threads;
+    add_kernel<R><<<blocks, threads, 0, e->stream>>>(static_cast<R*>(e->W), static_cast<const R*>(e->dW), fa);
     return cudaGetLastError();
 }
 
@@ -402,7 +427,7 @@ static int finish_shared_step(rsrl_engine* e, int n_blocks) {
     else CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_reduce<float>(e, n_blocks, xch) : launch_reduce<double>(e, n_blocks, xch));
     e->launches += 1;
     if (xch) {
-        ncclResult_t r = g_nccl.AllReduce(e->dW, e->dW, (size_t)e->FA, e->cfg.dtype == RSRL_F32 ? ncclFloat32 : ncclFloat64,
+        ncclResult_t r = g_nccl.AllReduce(e->dW, e->dW, (size_t)e->FA * e->WT, e->cfg.dtype == RSRL_F32 ? ncclFloat32 : ncclFloat64,
                                           ncclSum, e->comm, e->stream);
         if (r != ncclSuccess) return fail(RSRL_ECOMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
         CU_TRY(e->cfg.dtype == RSRL_F32 ? launch_add<float>(e) : launch_add<double>(e));
@@ -532,7 +557,12 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     e->N = cfg->n_envs; e->NG = cfg->n_envs_global > 0 ? cfg->n_envs_global : cfg->n_envs;
     e->F = n_features(cfg); e->FA = e->F * e->AW;
     e->has_trace = algo_has_trace(cfg->algo);
+    e->WT = algo_two_tables(cfg->algo) ? 2 : 1;
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
+    if (e->WT == 2 && (e->tile || e->f4)) {
+        delete e;
+        return fail(RSRL_EUNSUPPORTED, "GreedyGQ / A2C are built for the Fourier / Polynomial bases of the register path");
+    }
     e->epsilon = cfg->epsilon;
     {
         cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
@@ -594,7 +624,7 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     E_TRY(cudaMalloc(&e->last_len, N * sizeof(int32_t)));
     E_TRY(cudaMalloc(&e->len_hash, N * sizeof(unsigned long long)));
     if (cfg->record_td_error) E_TRY(cudaMalloc(&e->td, N * e->rsz));
-    E_TRY(cudaMalloc(&e->W, wcount(e) * e->rsz));
+    E_TRY(cudaMalloc(&e->W, wcount(e) * e->WT * e->rsz));
     if (e->has_trace) E_TRY(cudaMalloc(&e->z, (size_t)e->FA * N * e->rsz));
     if (e->tile) {
         e->targs.tp = tile_params(cfg);
@@ -614,8 +644,8 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         E_TRY(cudaMalloc(&e->partials, (size_t)(e->f4_nseg > e->f4tc_dw_grid ? e->f4_nseg : e->f4tc_dw_grid) * e->FA * e->rsz));
         E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
     } else if (cfg->weight_mode == RSRL_SHARED) {
-        E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->rsz));
-        E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->rsz));
+        E_TRY(cudaMalloc(&e->partials, (size_t)e->grid * e->FA * e->WT * e->rsz));
+        E_TRY(cudaMalloc(&e->dW, (size_t)e->FA * e->WT * e->rsz));
     }
     if (e->persistent && cfg->weight_mode == RSRL_SHARED) {
         const size_t rows = e->has_trace ? (size_t)e->FA : (size_t)e->F;       // reduce rows
@@ -647,7 +677,8 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     if (!e->tile && !e->f4) {
         StepArgs a = make_args(e);
         a.n = 0;
-        cudaError_t pe = dispatch_fused(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream);
+        cudaError_t pe = e->WT == 2 ? dispatch_two(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream)
+                                    : dispatch_fused(e->key, cfg->weight_mode, false, a, 1, e->block, e->smem, e->stream);
         if (pe == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); rsrl_engine_destroy(e); return unsupported(cfg); }
         E_TRY(pe);
         E_TRY(cudaStreamSynchronize(e->stream));
@@ -664,7 +695,7 @@ int rsrl_engine_reset(rsrl_engine_t* e, const double* init_states) {
     CU_TRY(cudaSetDevice(e->cfg.device));
     const size_t N = (size_t)e->N;
     cudaStream_t st = e->stream;
-    CU_TRY(cudaMemsetAsync(e->W, 0, wcount(e) * e->rsz, st));  // LFA::vector => Array2::zeros (examples/q_learning.rs:25)
+    CU_TRY(cudaMemsetAsync(e->W, 0, wcount(e) * e->WT * e->rsz, st));  // LFA::vector => Array2::zeros (examples/q_learning.rs:25)
     if (e->z) CU_TRY(cudaMemsetAsync(e->z, 0, (size_t)e->FA * N * e->rsz, st));
     if (e->td) CU_TRY(cudaMemsetAsync(e->td, 0, N * e->rsz, st));
     CU_TRY(cudaMemsetAsync(e->actions, 0xFF, N * sizeof(int32_t), st));  // -1
@@ -753,7 +784,8 @@ int rsrl_engine_step(rsrl_engine_t* e, int64_t k_steps) {
     { int rc = need_comm(e); if (rc) return rc; }
     for (int64_t k = 0; k < k_steps; ++k) {
         StepArgs a = make_args(e);
-        CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream));
+        CU_TRY(e->WT == 2 ? dispatch_two(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream)
+                          : dispatch_fused(e->key, e->cfg.weight_mode, false, a, e->grid, e->block, e->smem, e->stream));
         e->launches += 1;
         if (e->cfg.weight_mode == RSRL_SHARED) {
             int rc = finish_shared_step(e, e->grid);
@@ -845,6 +877,20 @@ int rsrl_engine_set_weights(rsrl_engine_t* e, const double* in) {
     const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
     return import_tensor(e, e->W, pe ? e->N : 1, e->FA, pe, in);
 }
+int rsrl_engine_get_aux_weights(rsrl_engine_t* e, double* out) {
+    if (!e || !out) return fail(RSRL_EINVAL, "null argument");
+    if (e->WT != 2) return fail(RSRL_EINVAL, "the configured agent has one weight table (aux weights: GreedyGQ fa_td, A2C policy)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    return export_tensor(e, static_cast<const char*>(e->W) + wcount(e) * e->rsz, pe ? e->N : 1, e->FA, pe, out);
+}
+int rsrl_engine_set_aux_weights(rsrl_engine_t* e, const double* in) {
+    if (!e || !in) return fail(RSRL_EINVAL, "null argument");
+    if (e->WT != 2) return fail(RSRL_EINVAL, "the configured agent has one weight table (aux weights: GreedyGQ fa_td, A2C policy)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    return import_tensor(e, static_cast<char*>(e->W) + wcount(e) * e->rsz, pe ? e->N : 1, e->FA, pe, in);
+}
 int rsrl_engine_get_traces(rsrl_engine_t* e, double* out) {
     if (!e || !out) return fail(RSRL_EINVAL, "null argument");
     if (!e->z) return fail(RSRL_EINVAL, "the configured algorithm has no eligibility trace");
@@ -911,7 +957,9 @@ static int engine_eval(rsrl_engine* e, int mode, int64_t n, const double* states
     CU_TRY(cudaMemcpyAsync(ds.p, states, (size_t)n * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     EvalArgs ea;
     memset(&ea, 0, sizeof ea);
-    ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.W = e->W; ea.w_env_stride = pe ? 1 : 0;
+    ea.mode = mode; ea.n = n; ea.states = ds.as<double>(); ea.w_env_stride = pe ? 1 : 0;
+    // Policy::sample / mode of the A2C agent go through the Gibbs policy's own table; evaluate() is the critic's Q
+    ea.W = (e->cfg.algo == RSRL_A2C && mode != 1) ? static_cast<const char*>(e->W) + wcount(e) * e->rsz : e->W;
     ea.out = mode == 1 ? dout.as<double>() : nullptr; ea.act_out = mode == 1 ? nullptr : dout.as<int32_t>();
     ea.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed); ea.draw = draw; ea.env_offset = e->cfg.env_offset; ea.counters = e->counters;
     if (e->tile) CU_TRY((e->cfg.dtype == RSRL_F32 ? launch_tile_eval_f32 : launch_tile_eval_f64)(e->cfg.domain, e->AW, ea, e->targs.tp, e->stream));
@@ -977,7 +1025,8 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
         e->tile_steps += 1;
     } else {
     const int grid = (int)((n + e->block - 1) / e->block);
-    CU_TRY(dispatch_fused(e->key, e->cfg.weight_mode, true, a, grid, e->block, e->smem, st));
+    CU_TRY(e->WT == 2 ? dispatch_two(e->key, e->cfg.weight_mode, true, a, grid, e->block, e->smem, st)
+                      : dispatch_fused(e->key, e->cfg.weight_mode, true, a, grid, e->block, e->smem, st));
     e->launches += 1;
     if (e->cfg.weight_mode == RSRL_SHARED) {
         int rc = finish_shared_step(e, grid);
@@ -994,6 +1043,50 @@ int rsrl_engine_handle(rsrl_engine_t* e, int64_t n, const double* from_states, c
         e->launches += 1;
         CU_TRY(cudaMemcpyAsync(td_out, e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    CU_TRY(cudaStreamSynchronize(st));
+    return RSRL_OK;
+}
+
+// ---- Domain::rollout ----
+int rsrl_engine_rollout(rsrl_engine_t* e, int64_t n, const double* init_states, int64_t step_limit, int32_t greedy, uint64_t draw,
+                        double* start_out, double* next_out, int32_t* actions_out, double* rewards_out, uint8_t* terminal_out,
+                        int32_t* len_out) {
+    if (!e || n <= 0 || step_limit < 1 || !start_out || !next_out || !actions_out || !rewards_out || !terminal_out || !len_out)
+        return fail(RSRL_EINVAL, "bad argument (step_limit >= 1)");
+    if (e->tile || e->f4) return fail(RSRL_EUNSUPPORTED, "rollout is built for the Fourier / Polynomial bases of the register path");
+    if (algo_td_pred(e->cfg.algo)) return fail(RSRL_EINVAL, "TD prediction engines have no Q-based policy");
+    const bool pe = e->cfg.weight_mode == RSRL_PER_ENV;
+    if (pe && n != e->N) return fail(RSRL_EINVAL, "PER_ENV weights: n must equal n_envs (rollout i follows agent i)");
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    const int64_t t_max = step_limit - 1 > 1 ? step_limit - 1 : 1;
+    DevBuf dinit, dstart, dnext, dact, drew, dterm, dlen;
+    const size_t sb = (size_t)n * e->D * sizeof(double), rows = (size_t)n * t_max;
+    if (init_states) { CU_TRY(dinit.alloc(sb)); CU_TRY(cudaMemcpyAsync(dinit.p, init_states, sb, cudaMemcpyHostToDevice, e->stream)); }
+    CU_TRY(dstart.alloc(sb)); CU_TRY(dnext.alloc(rows * e->D * sizeof(double))); CU_TRY(dact.alloc(rows * sizeof(int32_t)));
+    CU_TRY(drew.alloc(rows * sizeof(double))); CU_TRY(dterm.alloc(rows)); CU_TRY(dlen.alloc(n * sizeof(int32_t)));
+    RolloutArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.n = n; ra.env_offset = e->cfg.env_offset; ra.t_max = t_max; ra.take = step_limit - 1;
+    ra.init = init_states ? dinit.as<double>() : nullptr;
+    ra.W = e->cfg.algo == RSRL_A2C ? static_cast<const char*>(e->W) + wcount(e) * e->rsz : e->W;
+    ra.w_env_stride = pe ? 1 : 0;
+    ra.greedy = greedy != 0; ra.init_mode = e->cfg.init_mode; ra.draw = draw;
+    ra.pol = policy_of(e->cfg.policy, e->epsilon, e->cfg.seed);
+    for (int d = 0; d < RSRL_MAX_DIM; ++d) { ra.init_lo[d] = e->cfg.init_lo[d]; ra.init_hi[d] = e->cfg.init_hi[d]; }
+    ra.start_out = dstart.as<double>(); ra.next_out = dnext.as<double>(); ra.actions_out = dact.as<int32_t>();
+    ra.rewards_out = drew.as<double>(); ra.terminal_out = dterm.as<uint8_t>(); ra.len_out = dlen.as<int32_t>();
+    ra.counters = e->counters;
+    cudaError_t ce = dispatch_rollout(e->key, ra, e->stream);
+    if (ce == cudaErrorInvalidDeviceFunction) { cudaGetLastError(); return unsupported(&e->cfg); }
+    CU_TRY(ce);
+    e->launches += 1;
+    cudaStream_t st = e->stream;
+    CU_TRY(cudaMemcpyAsync(start_out, dstart.p, sb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(next_out, dnext.p, rows * e->D * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(actions_out, dact.p, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(rewards_out, drew.p, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(terminal_out, dterm.p, rows, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(len_out, dlen.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return RSRL_OK;
 }

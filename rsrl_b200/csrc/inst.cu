@@ -93,6 +93,27 @@ static cudaError_t persist_one(const StepArgs& a, int k_steps, const SyncArgs& s
     return cudaGetLastError();
 }
 
+template <int BASIS, int P, int MODE, bool EXT>
+static cudaError_t two_one(const StepArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = two_table_step_kernel<R, DOM, BASIS, P, MODE, EXT>;
+    static size_t configured[64] = {0};
+    int dev;
+    if (!smem_configured(configured, smem, &dev)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = smem;
+    }
+    kern<<<grid, block, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int BASIS, int P>
+static cudaError_t rollout_one(const RolloutArgs& ra, cudaStream_t st) {
+    const int block = 128, grid = (int)((ra.n + block - 1) / block);
+    rollout_kernel<R, DOM, BASIS, P><<<grid, block, 0, st>>>(ra);
+    return cudaGetLastError();
+}
+
 template <int BASIS, int P, int AW>
 static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
     const int block = 128;
@@ -143,6 +164,31 @@ cudaError_t RSRL_CAT(launch_persist_, RSRL_SUFFIX)(const BasisKey& k, int mode, 
         if (k.aw == A) return RSRL_PERSIST(B, P, A); \
         if (k.aw == 1) return RSRL_PERSIST(B, P, 1); \
     }
+    RSRL_COMBOS(X)
+#undef X
+    return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t RSRL_CAT(launch_two_, RSRL_SUFFIX)(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid, int block, size_t smem,
+                                               cudaStream_t st) {
+#if RSRL_DOM == 0 && !defined(RSRL_EMPTY)
+    // GreedyGQ / A2C are instantiated for MountainCar (the domain of examples/greedy_gq.rs and examples/a2c.rs): the D = 4 bases
+    // would add ten minutes of compile time for 256-feature fully unrolled kernels nobody asked for
+#define X(B, P)                                                                                                                  \
+    if (k.basis == B && k.order == P) {                                                                                          \
+        if (mode == RSRL_SHARED) return ext ? two_one<B, P, RSRL_SHARED, true>(a, grid, block, smem, st)                          \
+                                            : two_one<B, P, RSRL_SHARED, false>(a, grid, block, smem, st);                        \
+        return ext ? two_one<B, P, RSRL_PER_ENV, true>(a, grid, block, smem, st) : two_one<B, P, RSRL_PER_ENV, false>(a, grid, block, smem, st); \
+    }
+    RSRL_COMBOS(X)
+#undef X
+#endif
+    return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t RSRL_CAT(launch_rollout_, RSRL_SUFFIX)(const BasisKey& k, const RolloutArgs& ra, cudaStream_t st) {
+#define X(B, P) \
+    if (k.basis == B && k.order == P) return rollout_one<B, P>(ra, st);
     RSRL_COMBOS(X)
 #undef X
     return cudaErrorInvalidDeviceFunction;

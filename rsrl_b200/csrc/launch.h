@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "persistent.cuh"
+#include "twotable.cuh"
 
 namespace rsrl {
 
@@ -36,7 +37,13 @@ typedef cudaError_t (*eval_launch_fn)(const BasisKey&, const EvalArgs&, cudaStre
 typedef cudaError_t (*persist_launch_fn)(const BasisKey&, int weight_mode, const StepArgs&, int k_steps, const SyncArgs&,
                                          const PeerArgs&, int grid, int block, size_t smem, cudaStream_t, int* max_clusters);
 
+// two-table agents (GreedyGQ, A2C) and Domain::rollout
+typedef cudaError_t (*two_launch_fn)(const BasisKey&, int weight_mode, bool ext, const StepArgs&, int grid, int block, size_t smem, cudaStream_t);
+typedef cudaError_t (*rollout_launch_fn)(const BasisKey&, const RolloutArgs&, cudaStream_t);
+
 #define RSRL_DECL_INST(SUFFIX)                                                                                      \
+    cudaError_t launch_two_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t);   \
+    cudaError_t launch_rollout_##SUFFIX(const BasisKey&, const RolloutArgs&, cudaStream_t);                         \
     cudaError_t launch_fused_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t); \
     cudaError_t launch_eval_##SUFFIX(const BasisKey&, const EvalArgs&, cudaStream_t);                                 \
     cudaError_t launch_persist_##SUFFIX(const BasisKey&, int, const StepArgs&, int, const SyncArgs&, const PeerArgs&, int, int, size_t, cudaStream_t, int*);

@@ -98,6 +98,30 @@ class Engine:
         assert w.shape == self._wshape()
         check(self.lib.rsrl_engine_set_weights(self.h, dp(w)))
 
+    def aux_weights(self):
+        """second weight table: GreedyGQ fa_td (greedy_gq.rs:52), A2C the Gibbs policy's LFA (a2c.rs:27-31)"""
+        out = np.empty(self._wshape())
+        check(self.lib.rsrl_engine_get_aux_weights(self.h, dp(out)))
+        return out
+
+    def set_aux_weights(self, w):
+        w = _f64(w)
+        assert w.shape == self._wshape()
+        check(self.lib.rsrl_engine_set_aux_weights(self.h, dp(w)))
+
+    def rollout(self, n=None, init_states=None, step_limit=500, greedy=True, draw=0):
+        """Domain::rollout for n envs with the current weights (rsrl_domains/src/lib.rs:448-479).  Returns a dict in the
+        Trajectory{start, steps} layout: start (n, D), next (n, T, D), actions / rewards / terminal (n, T), len (n,)."""
+        n = self.N if n is None else n
+        T = max(step_limit - 1, 1)
+        init = None if init_states is None else _f64(init_states)
+        out = dict(start=np.zeros((n, self.D)), next=np.zeros((n, T, self.D)), actions=np.full((n, T), -1, dtype=np.int32),
+                   rewards=np.zeros((n, T)), terminal=np.zeros((n, T), dtype=np.uint8), len=np.zeros(n, dtype=np.int32))
+        check(self.lib.rsrl_engine_rollout(self.h, n, None if init is None else dp(init), step_limit, 1 if greedy else 0, draw,
+                                           dp(out["start"]), dp(out["next"]), ip(out["actions"]), dp(out["rewards"]),
+                                           u8p(out["terminal"]), ip(out["len"])))
+        return out
+
     def traces(self):
         out = np.empty((self.N, self.F, self.AW))
         check(self.lib.rsrl_engine_get_traces(self.h, dp(out)))
@@ -213,6 +237,55 @@ def domain_is_terminal(domain, states):
     t = np.empty(s.shape[0], dtype=np.uint8)
     check(abi.load().rsrl_domain_is_terminal(domain, s.shape[0], dp(s), u8p(t)))
     return t
+
+
+def _check_ex(code):
+    if code != abi.OK:
+        msg = abi.load().rsrl_domain_ex_last_error()
+        raise abi.RsrlError(code, msg.decode() if msg else "")
+
+
+def domain_ex_info(domain):
+    d, a = C.c_int32(), C.c_int32()
+    lo, hi, st = np.zeros(6), np.zeros(6), np.zeros(6)
+    _check_ex(abi.load().rsrl_domain_ex_info(domain, C.byref(d), C.byref(a), dp(lo), dp(hi), dp(st)))
+    return d.value, a.value, lo[:d.value].copy(), hi[:d.value].copy(), st[:d.value].copy()
+
+
+def domain_ex_step(domain, states, actions):
+    """ContinuousMountainCar (actions: forces, f64) / HIVTreatment (actions: indices). Returns (states, obs, rewards, terminal)."""
+    D = 6 if domain == abi.HIV else 2
+    ns = _f64(states).reshape(-1, D).copy()
+    n = ns.shape[0]
+    obs, r, t = np.zeros_like(ns), np.zeros(n), np.zeros(n, dtype=np.uint8)
+    if domain == abi.HIV:
+        a = _i32(actions)
+        _check_ex(abi.load().rsrl_domain_ex_step(domain, n, dp(ns), ip(a), None, dp(obs), dp(r), u8p(t)))
+    else:
+        a = _f64(actions)
+        _check_ex(abi.load().rsrl_domain_ex_step(domain, n, dp(ns), None, dp(a), dp(obs), dp(r), u8p(t)))
+    return ns, obs, r, t
+
+
+def domain_ex_emit(domain, states):
+    D = 6 if domain == abi.HIV else 2
+    s = _f64(states).reshape(-1, D)
+    obs, t = np.zeros_like(s), np.zeros(s.shape[0], dtype=np.uint8)
+    _check_ex(abi.load().rsrl_domain_ex_emit(domain, s.shape[0], dp(s), dp(obs), u8p(t)))
+    return obs, t
+
+
+def weights_to_serde(weights):
+    """The `serde` feature's on-disk form of Parameterised::weights() (rsrl/Cargo.toml:26): ndarray 0.13's serde layout of an
+    Array2<f64> — {"v": 1, "dim": [rows = F, cols = A], "data": row-major} (the layout rsrl_engine_get_weights already returns)."""
+    w = _f64(weights)
+    assert w.ndim == 2
+    return {"v": 1, "dim": [int(w.shape[0]), int(w.shape[1])], "data": [float(x) for x in w.ravel()]}
+
+
+def weights_from_serde(obj):
+    assert obj["v"] == 1 and len(obj["dim"]) == 2
+    return np.asarray(obj["data"], dtype=np.float64).reshape(obj["dim"])
 
 
 def basis_project(cfg, states):

@@ -786,7 +786,7 @@ def test_multi_gpu_peer_exchange_matches_single_gpu(E):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     world = 2 if n < 4 else 4
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "multi_gpu_check.py")],
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "tools", "multi_gpu_check.py")],
                          capture_output=True, text=True, timeout=900)
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
@@ -882,3 +882,167 @@ def test_error_behaviour(E):
     assert ei.value.code == abi.ENONFINITE
     r, t = np.zeros(1), np.zeros(1, dtype=np.uint8)
     assert lib.rsrl_domain_step(9, 1, abi.dp(np.zeros((1, 2))), abi.ip(np.zeros(1, dtype=np.int32)), abi.dp(r), abi.u8p(t)) == abi.EINVAL
+
+
+# ---------------------------------------------------------------------------------------------
+# GreedyGQ, A2C (Softmax grad_log), Domain::rollout / Trajectory
+# ---------------------------------------------------------------------------------------------
+TWO_TABLE = [
+    ("greedy_gq", dict(algo=abi.GREEDY_GQ, policy=abi.EPSILON_GREEDY, epsilon=0.1, basis_order=3, lr=0.1, alpha=0.001, gamma=0.99)),   # examples/greedy_gq.rs:25-38
+    ("a2c", dict(algo=abi.A2C, policy=abi.SOFTMAX, epsilon=1.0, basis_order=3, lr=0.001, alpha=0.001, gamma=1.0)),                    # examples/a2c.rs:24-48
+    ("a2c_fast", dict(algo=abi.A2C, policy=abi.SOFTMAX, epsilon=0.5, basis_order=5, lr=0.05, alpha=0.05, gamma=0.99)),
+]
+
+
+@pytest.mark.parametrize("name,kw", TWO_TABLE, ids=[t[0] for t in TWO_TABLE])
+@pytest.mark.parametrize("mode", [abi.SHARED, abi.PER_ENV], ids=["shared", "per_env"])
+def test_two_table_agents_free_run_f64(E, oracle, name, kw, mode):
+    """GreedyGQ (control/td/greedy_gq.rs:73-141) and A2C (examples/a2c.rs) free-running against the oracle, dtype f64:
+    actions / step counts bit-exact, both weight tables within 1e-9."""
+    cfg = _mc_cfg(weight_mode=mode, update_scale=abi.SCALE_MEAN if mode == abi.SHARED else abi.SCALE_SUM, n_envs=300,
+                  max_episode_steps=120, **kw)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        # a2c_fast with one agent per env: the policy-gradient dynamics at these step sizes amplify a 1e-16 difference (exp of CUDA vs
+        # glibc) by ~1.3x per step (tests/tools/diag_a2c.py: 1e-9 after 75 steps) — compare over a horizon where it is still small
+        for chunk in ((1, 9, 40) if (name == "a2c_fast" and mode == abi.PER_ENV) else (1, 9, 250)):
+            e.step(chunk)
+            o.step(chunk)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9)
+            aw, ow = e.aux_weights(), o.aux_weights()
+            assert np.abs(aw - ow).max() < 1e-9 * max(1.0, np.abs(ow).max())
+        assert np.abs(o.aux_weights()).max() > 0 and (o.stats()["total_episodes"] > 0 or o.stats()["batch_steps"] < 120)
+
+
+def test_greedy_gq_example_single_env(E, oracle):
+    """examples/greedy_gq.rs as written: one env from MountainCar::default(), Fourier(3), SGD(0.1) / SGD(0.001), eps 0.1, gamma 0.99,
+    1000-step cap; N = 1 is op for op the reference loop."""
+    cfg = abi.default_config(n_envs=1, dtype=abi.F64, basis_order=3, algo=abi.GREEDY_GQ, policy=abi.EPSILON_GREEDY, epsilon=0.1, lr=0.1,
+                             alpha=0.001, gamma=0.99, max_episode_steps=1000, record_td_error=1)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(6000)
+        o.step(6000)
+        e.sync()
+        _compare_engines(e, o, w_tol=1e-9, s_tol=1e-8)
+        assert o.stats()["terminal_episodes"] > 3      # it learns to reach the goal
+
+
+def test_two_table_f32_teacher_forced(E, oracle):
+    """fp32 tables against the f64 oracle, one step at a time from the device's state and weights."""
+    for name, kw in TWO_TABLE[:2]:
+        cfg = _mc_cfg(dtype=abi.F32, n_envs=512, update_scale=abi.SCALE_MEAN, **kw)
+        rng = np.random.default_rng(3)
+        with E.Engine(cfg) as e:
+            o = oracle.Engine(cfg)
+            e.set_weights(rng.normal(size=(16, 3)) * 0.3)
+            e.set_aux_weights(rng.normal(size=(16, 3)) * 0.3)
+            for t in range(10):
+                o.set_states(e.states())
+                o.set_weights(e.weights())
+                o.set_aux_weights(e.aux_weights())
+                e.step(1)
+                o.step(1)
+                e.sync()
+                same = e.actions() == o.actions()
+                assert same.mean() > 0.97
+                assert np.abs(e.td_errors()[same] - o.td_errors()[same]).max() < 2e-5 * max(1.0, np.abs(o.td_errors()).max())
+                if same.all():
+                    assert np.abs(e.weights() - o.weights()).max() < 2e-6 and np.abs(e.aux_weights() - o.aux_weights()).max() < 2e-6
+
+
+def test_two_table_handle_and_policy_entry_points(E, oracle):
+    """Handler<&Transition>::handle for GreedyGQ, Policy::sample / mode of the A2C agent (they read the policy's own table)."""
+    rng = np.random.default_rng(9)
+    lo, hi = oracle.domain_limits(MC)
+    s = rng.uniform(lo, hi, size=(200, 2))
+    a = rng.integers(0, 3, 200).astype(np.int32)
+    ns, r, term = oracle.domain_step(MC, s, a)
+    cfg = _mc_cfg(n_envs=200, **TWO_TABLE[0][1])
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        Wq, Wt = rng.normal(size=(16, 3)), rng.normal(size=(16, 3))
+        for x in (e, o):
+            x.set_weights(Wq)
+            x.set_aux_weights(Wt)
+        td_e, td_o = e.handle(s, a, r, ns, term, draw_idx=1), o.handle(s, a, r, ns, term, draw_idx=1)
+        assert np.abs(td_e - td_o).max() < 1e-12
+        assert np.abs(e.weights() - o.weights()).max() < 1e-11 and np.abs(e.aux_weights() - o.aux_weights()).max() < 1e-11
+    cfg = _mc_cfg(n_envs=200, **TWO_TABLE[1][1])
+    with E.Engine(cfg) as e:
+        Wp = rng.normal(size=(16, 3))
+        e.set_weights(rng.normal(size=(16, 3)))
+        e.set_aux_weights(Wp)
+        h = oracle.evaluate(cfg, Wp, s)
+        assert (e.sample(s, draw=3) == oracle.policy_sample_batch(abi.SOFTMAX, 1.0, cfg.seed, 3, 0, h)).all()
+        probs = np.exp(h - h.max(axis=1, keepdims=True))
+        assert (e.mode(s) == np.argmax(probs, axis=1)).mean() > 0.99   # argmax_first over the probabilities (softmax.rs:141)
+    with pytest.raises(abi.RsrlError) as ei:
+        E.Engine(_mc_cfg(algo=abi.A2C, policy=abi.GREEDY))
+    assert ei.value.code == abi.EINVAL
+
+
+@pytest.mark.parametrize("dtype", [abi.F64, abi.F32], ids=["f64", "f32"])
+def test_rollout_matches_oracle(E, oracle, dtype):
+    """Domain::rollout (rsrl_domains/src/lib.rs:448-479) for a batch of envs with learned weights: Trajectory{start, steps}
+    layout, mode() policy (examples/q_learning.rs:57) and sampled policy; step-limit and terminal semantics."""
+    cfg = _mc_cfg(dtype=dtype, n_envs=400, policy=abi.EPSILON_GREEDY, epsilon=0.1, update_scale=abi.SCALE_MEAN, lr=0.5)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.step(300)
+        e.sync()
+        o.set_weights(e.weights())
+        rng = np.random.default_rng(1)
+        init = np.column_stack([rng.uniform(-1.2, 0.59, 400), rng.uniform(-0.07, 0.07, 400)])
+        for greedy, limit in ((True, 120), (False, 40), (True, 1), (True, 2)):
+            re, ro = e.rollout(init_states=init, step_limit=limit, greedy=greedy, draw=7), o.rollout(init_states=init, step_limit=limit, greedy=greedy, draw=7)
+            assert (re["start"] == init).all()
+            if dtype == abi.F64:
+                assert (re["len"] == ro["len"]).all()
+                for i in range(400):
+                    n = re["len"][i]
+                    assert (re["actions"][i, :n] == ro["actions"][i, :n]).all() and (re["terminal"][i, :n] == ro["terminal"][i, :n]).all()
+                    assert (re["rewards"][i, :n] == ro["rewards"][i, :n]).all() and np.abs(re["next"][i, :n] - ro["next"][i, :n]).max(initial=0) < 1e-12
+            else:   # fp32 Q: a near-tie may flip a greedy action and change the trajectory from there on
+                assert (re["len"] == ro["len"]).mean() > 0.9
+            n = re["len"]
+            assert (n <= max(limit - 1, 0)).all() and (limit < 2 or (n >= 1).all())
+            j = np.arange(re["terminal"].shape[1])[None, :]
+            assert not (re["terminal"].astype(bool) & (j < n[:, None] - 1)).any()      # only the last recorded observation can be terminal
+        # default start (config's distribution): Trajectory of examples/q_learning.rs:57
+        rd = e.rollout(n=5, step_limit=30, greedy=True, draw=0)
+        od = o.rollout(n=5, step_limit=30, greedy=True, draw=0)
+        assert np.abs(rd["start"] - od["start"]).max() < 1e-15 and (dtype == abi.F32 or (rd["len"] == od["len"]).all())
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8f-4: ContinuousMountainCar / HIVTreatment as batched Domain::step / emit
+# ---------------------------------------------------------------------------------------------
+def test_extended_domains_match_oracle(E, oracle):
+    CMC, HIV = abi.CONTINUOUS_MOUNTAIN_CAR, abi.HIV
+    assert E.domain_ex_info(CMC)[:2] == (2, 0) and E.domain_ex_info(HIV)[:2] == (6, 4)
+    assert (E.domain_ex_info(HIV)[4] == oracle.domain_ex_default(HIV)).all()
+    rng = np.random.default_rng(2)
+    # ContinuousMountainCar: reference terminal-predicate cases (continuous.rs:105-122) + random trajectories
+    cases = np.array([[-0.5, 0.0], [0.6, -0.05], [0.6, 0.0], [0.6, 0.05], [0.6 - 0.0001 * 0.6, 0.0], [0.6 + 0.0001 * 0.6, 0.0]])
+    assert (E.domain_ex_emit(CMC, cases)[1] == [0, 1, 1, 1, 0, 1]).all()
+    s = np.column_stack([rng.uniform(-1.2, 0.6, 3000), rng.uniform(-0.07, 0.07, 3000)])
+    for _ in range(20):
+        a = rng.uniform(-2.0, 2.0, 3000)     # beyond [-1, 1]: clipped like Interval::map_onto
+        ns, obs, r, t = E.domain_ex_step(CMC, s, a)
+        ns2, obs2, r2, t2 = oracle.domain_ex_step(CMC, s, a)
+        assert np.abs(ns - ns2).max() < 1e-15 and (r == r2).all() and (t == t2).all() and (obs == ns).all()
+        s = ns
+    # HIV: reference observation cases (hiv.rs:156-204) + steps under every action from states around the default
+    obs, t = E.domain_ex_emit(HIV, [[1.0, 10.0, 100.0, 200.0, 500.0, 10000.0], [1e10, 1e-10, 1.0, 1.0, 1.0, 1.0]])
+    assert np.abs(obs[0] - [0.0, 1.0, 2.0, 2.301029995663981, 2.698970004336019, 4.0]).max() < 1e-7 and t.sum() == 0
+    assert np.abs(obs[1] - [8.0, -5.0, 0.0, 0.0, 0.0, 0.0]).max() < 1e-7
+    s = oracle.domain_ex_default(HIV)[None, :] * rng.uniform(0.5, 2.0, size=(64, 6))
+    a = rng.integers(0, 4, 64).astype(np.int32)
+    for _ in range(2):
+        ns, obs, r, t = E.domain_ex_step(HIV, s, a)
+        ns2, obs2, r2, t2 = oracle.domain_ex_step(HIV, s, a)
+        assert (np.abs(ns - ns2) / np.abs(ns2)).max() < 1e-11      # 4000 gradient evaluations per step, unfused f64 on both sides
+        assert np.abs(obs - obs2).max() < 1e-11 and np.abs(r - r2).max() < 1e-12 and t.sum() == 0
+        s = ns

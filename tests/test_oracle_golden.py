@@ -284,3 +284,157 @@ def test_softmax_sampling(oracle):
     for _ in range(20000):
         counts[oracle.policy_sample(abi.SOFTMAX, 1.0, q, rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32))[0]] += 1
     assert np.abs(counts / 20000 - [p0, 1 - p0]).max() < 1e-2            # test_2d
+
+
+# ---- GreedyGQ / A2C / rollout: the C oracle against independent numpy restatements of the reference text ----
+def test_oracle_greedy_gq_matches_independent_restatement(oracle):
+    """control/td/greedy_gq.rs:73-141 restated in numpy: three updates per transition on two weight tables."""
+    cfg = abi.default_config(algo=abi.GREEDY_GQ, policy=abi.EPSILON_GREEDY, epsilon=0.1, basis_order=3, lr=0.1, alpha=0.001, gamma=0.99,
+                             n_envs=96, dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[0.55, 0.07], seed=5,
+                             record_td_error=1)
+    rng = np.random.default_rng(0)
+    o = oracle.Engine(cfg)
+    Wq, Wt = rng.normal(size=(16, 3)) * 0.3, rng.normal(size=(16, 3)) * 0.3
+    o.set_weights(Wq)
+    o.set_aux_weights(Wt)
+    s = o.states().copy()
+    s[::3] = np.column_stack([rng.uniform(0.56, 0.6, 32), rng.uniform(0.05, 0.07, 32)])   # a third of the envs reach the goal in this step
+    o.set_states(s)
+    o.step(1)
+    a, td = o.actions(), o.td_errors()
+    ns, r, term = oracle.domain_step(abi.MOUNTAIN_CAR, s, a)
+    assert term.any() and not term.all()      # both branches of handle()
+    phi, nphi = oracle.project(cfg, s), oracle.project(cfg, ns)
+    Q, V, NQ = phi @ Wq, phi @ Wt, nphi @ Wq
+    dq, dt = np.zeros_like(Wq), np.zeros_like(Wt)
+    for i in range(96):
+        qsa, td_est = Q[i, a[i]], V[i, a[i]]
+        if term[i]:
+            e = r[i] - qsa
+        else:
+            na = max(range(3), key=lambda j: (NQ[i, j], j))   # find_max: last maximal index (core.rs:96-105)
+            e = r[i] + 0.99 * NQ[i, na] - qsa
+            dq[:, na] += 0.1 * (-0.99 * td_est) * nphi[i]
+        dq[:, a[i]] += 0.1 * e * phi[i]
+        dt[:, a[i]] += 0.001 * (e - td_est) * phi[i]
+        assert abs(e - td[i]) < 1e-12
+    assert np.abs(o.weights() - (Wq + dq)).max() < 1e-12 and np.abs(o.aux_weights() - (Wt + dt)).max() < 1e-12
+
+
+def test_oracle_a2c_matches_independent_restatement(oracle):
+    """examples/a2c.rs:37-58 with control/ac.rs:100-114 and policies/softmax.rs:113-129 restated in numpy for ONE agent per env
+    (PER_ENV weights = the reference's in-place updates): SARSA critic, then the policy update with the critic closure
+    evaluated on the updated Q."""
+    cfg = abi.default_config(algo=abi.A2C, policy=abi.SOFTMAX, epsilon=1.0, basis_order=3, lr=0.05, alpha=0.02, gamma=1.0, n_envs=40,
+                             weight_mode=abi.PER_ENV, dtype=abi.F64, init_mode=abi.INIT_UNIFORM, init_lo=[-0.6, 0.0], init_hi=[0.55, 0.07],
+                             seed=6, record_td_error=1)
+    rng = np.random.default_rng(1)
+    o = oracle.Engine(cfg)
+    Wq, Wp = rng.normal(size=(40, 16, 3)) * 0.3, rng.normal(size=(40, 16, 3)) * 0.5
+    o.set_weights(Wq)
+    o.set_aux_weights(Wp)
+    s = o.states().copy()
+    s[::4] = np.column_stack([rng.uniform(0.56, 0.6, 10), rng.uniform(0.05, 0.07, 10)])   # some terminal transitions
+    o.set_states(s)
+    o.step(1)
+    a, td = o.actions(), o.td_errors()
+    ns, r, term = oracle.domain_step(abi.MOUNTAIN_CAR, s, a)
+    assert term.any() and not term.all()
+    phi, nphi = oracle.project(cfg, s), oracle.project(cfg, ns)
+
+    def softmax(h):
+        v = np.exp(h - h.max())
+        return v / v.sum()
+    for i in range(40):
+        q, nq = phi[i] @ Wq[i], nphi[i] @ Wq[i]
+        # behaviour action: inverse CDF of softmax(theta^T phi(s)) with the env's 53-bit uniform (policies/mod.rs:46-61)
+        rnd = oracle.draw(cfg.seed, i, 0, 1)
+        u = ((int(rnd[0]) << 32 | int(rnd[1])) >> 11) / 2.0 ** 53
+        ps = softmax(phi[i] @ Wp[i])
+        assert a[i] == min(int(np.searchsorted(np.cumsum(ps), u, side="right")), 2)
+        if term[i]:
+            res = r[i] - q[a[i]]
+        else:
+            rn = oracle.draw(cfg.seed, i, 0, 2)
+            un = ((int(rn[0]) << 32 | int(rn[1])) >> 11) / 2.0 ** 53
+            na = min(int(np.searchsorted(np.cumsum(softmax(nphi[i] @ Wp[i])), un, side="right")), 2)
+            res = r[i] + 1.0 * nq[na] - q[a[i]]
+        assert abs(res - td[i]) < 1e-12
+        Wq_new = Wq[i].copy()
+        Wq_new[:, a[i]] += 0.05 * res * phi[i]
+        q2 = phi[i] @ Wq_new
+        adv = q2[a[i]] - q2 @ ps
+        sf = ps.copy()
+        sf[a[i]] -= 1.0
+        Wp_new = Wp[i] + (0.02 * adv) * np.outer(phi[i], -sf)
+        assert np.abs(o.weights()[i] - Wq_new).max() < 1e-12 and np.abs(o.aux_weights()[i] - Wp_new).max() < 1e-12
+
+
+def test_oracle_rollout_is_domain_rollout(oracle):
+    """rsrl_domains/src/lib.rs:448-479: start = emit(); the first step is always executed; steps stop after a terminal
+    observation; Some(limit) keeps limit - 1 steps (`iter.take(sl.saturating_sub(1))`)."""
+    cfg = abi.default_config(n_envs=3, dtype=abi.F64)
+    o = oracle.Engine(cfg)
+    W = np.zeros((36, 3))
+    W[-1, 2] = 1.0          # Q(s)[2] = 1 > others: mode() always pushes right
+    o.set_weights(W)
+    init = np.array([[-0.5, 0.0], [0.5, 0.06], [0.59, 0.07]])
+    r = o.rollout(init_states=init, step_limit=500)
+    assert (r["start"] == init).all()
+    assert (r["len"] == [499, 2, 1]).all()                       # env 0 is still climbing when the limit cuts it
+    for i in range(3):
+        n = r["len"][i]
+        s = init[i].copy()
+        for j in range(n):
+            s, rew, term = oracle.domain_step(abi.MOUNTAIN_CAR, s[None, :], [2])
+            s = s[0]
+            assert (r["next"][i, j] == s).all() and r["actions"][i, j] == 2 and r["rewards"][i, j] == rew[0] and r["terminal"][i, j] == term[0]
+        assert r["terminal"][i, :n - 1].sum() == 0 and (i == 0 or r["terminal"][i, n - 1] == 1)
+    assert (o.rollout(init_states=init, step_limit=1)["len"] == 0).all()     # take(0): the executed first step is not recorded
+    assert (o.rollout(init_states=init, step_limit=2)["len"] == 1).all()
+    total_reward = r["rewards"][1, :r["len"][1]].sum()                      # Trajectory::total_reward
+    assert total_reward == -1.0
+
+
+# ---- ContinuousMountainCar / HIVTreatment (SURVEY 8f-4): the reference's own unit tests on the oracle ----
+def test_continuous_mountain_car_reference_tests(oracle):
+    CMC = abi.CONTINUOUS_MOUNTAIN_CAR
+    assert (oracle.domain_ex_default(CMC) == [-0.5, 0.0]).all()                                     # continuous.rs:92-103
+    X_MAX = 0.6
+    cases = [([-0.5, 0.0], 0), ([X_MAX, -0.05], 1), ([X_MAX, 0.0], 1), ([X_MAX, 0.05], 1),            # continuous.rs:105-122
+             ([X_MAX - 0.0001 * X_MAX, 0.0], 0), ([X_MAX + 0.0001 * X_MAX, 0.0], 1)]
+    obs, term = oracle.domain_ex_emit(CMC, [c[0] for c in cases])
+    assert (term == [c[1] for c in cases]).all() and (obs == np.array([c[0] for c in cases])).all()
+    # the action is clipped onto [-1, 1]; FORCE_CAR = 0.0015 (continuous.rs:41-48)
+    s, _, r, t = oracle.domain_ex_step(CMC, [[-0.5, 0.0]] * 3, [5.0, 1.0, -0.25])
+    assert (s[0] == s[1]).all() and r[0] == -1.0 and t[0] == 0
+    assert abs(s[2][1] - (0.0015 * -0.25 - 0.0025 * np.cos(3 * -0.5))) < 1e-18
+
+
+def test_hiv_reference_tests(oracle):
+    HIV = abi.HIV
+    obs, term = oracle.domain_ex_emit(HIV, [[1.0, 10.0, 100.0, 200.0, 500.0, 10000.0]])           # hiv.rs:156-170
+    assert np.abs(obs[0] - [0.0, 1.0, 2.0, 2.301029995663981, 2.698970004336019, 4.0]).max() < 1e-7 and term[0] == 0
+    obs, _ = oracle.domain_ex_emit(HIV, [oracle.domain_ex_default(HIV)])                           # hiv.rs:172-187
+    assert np.abs(obs[0] - [5.213711618903007, 4.077186154085897, 0.698970004336019, 1.662757831681574, 4.805629971908577,
+                            1.380211241711606]).max() < 1e-7
+    obs, _ = oracle.domain_ex_emit(HIV, [[1e10, 1e-10, 1.0, 1.0, 1.0, 1.0]])                       # hiv.rs:189-204
+    assert np.abs(obs[0] - [8.0, -5.0, 0.0, 0.0, 0.0, 0.0]).max() < 1e-7
+    # one treatment step from the default (unhealthy steady) state: stays near it without drugs, reward follows hiv.rs:141-148
+    s0 = oracle.domain_ex_default(HIV)
+    s, o, r, t = oracle.domain_ex_step(HIV, [s0, s0], [0, 3])
+    assert np.abs(np.log10(s[0]) - np.log10(s0)).max() < 0.05 and t.sum() == 0
+    assert abs(r[0] - (1e3 * o[0][5] - 0.1 * o[0][4]) / 1e5) < 1e-15
+    assert abs(r[1] - (1e3 * o[1][5] - 0.1 * o[1][4] - 2e4 * 0.49 - 2e3 * 0.09) / 1e5) < 1e-12
+    assert s[1][4] < s[0][4]        # both drugs: the free virus count falls
+
+
+def test_serde_weight_layout():
+    """rsrl/Cargo.toml:26 `serde`: Array2<f64> weights serialise as ndarray's {"v", "dim", "data"} with row-major data == the F x A
+    layout of rsrl_engine_get_weights (Parameterised::weights_view, rsrl/src/params/mod.rs:116-134)."""
+    import json
+    from rsrl_b200.engine import weights_from_serde, weights_to_serde
+    W = np.arange(12, dtype=np.float64).reshape(4, 3) * 0.5
+    doc = json.loads(json.dumps(weights_to_serde(W)))
+    assert doc == {"v": 1, "dim": [4, 3], "data": [0.0, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5]}
+    assert (weights_from_serde(doc) == W).all()
