@@ -34,7 +34,7 @@ namespace {
 constexpr int kModeTrace = 2;  // persistent.cuh kModeSharedTrace
 
 struct Shape {
-    int persistent, mode, grid, cs, ncl, block, lpr, lpg, seg_len, pe_smem;
+    int persistent, mode, grid, cs, ncl, block, lpr, unused7, unused8, pe_smem;
     int fx;  // counting (fixed-point) exchange instead of the cluster + LL-line exchange
 };
 
@@ -135,16 +135,16 @@ void cta_step(Engine& e, int rank, int b, const StepArgs& a_rank, uint64_t t, fl
     const int64_t base = (int64_t)b * per_cta < N ? (int64_t)b * per_cta : N;
     const int64_t end = base + per_cta < N ? base + per_cta : N;
     const int n_chunks = SHAREDW ? (int)((per_cta + BLOCK - 1) / BLOCK) : 1;
-    const int lpg = sh.lpg, seg_len = sh.seg_len;
+    const int NW = BLOCK / 32;  // warps: the CTA reduce is warp-local (persistent.cuh)
 
     StepArgs a = a_rank;
     a.counters = cnt;
     a.n_ep = rs.n_ep.data(); a.last_len = rs.last_len.data(); a.len_hash = rs.len_hash.data();
 
-    std::vector<float> acc;  // [ROWS][NDC][lpg] reducer accumulators
+    std::vector<float> wpart;  // [NW][ROWS][NDC] warp partials
     std::vector<float> red, dcs;
     if (SHAREDW) {
-        acc.assign((size_t)ROWS * NDC * lpg, 0.0f);
+        wpart.assign((size_t)NW * ROWS * NDC, 0.0f);
         red.assign((size_t)ROWS * BLOCK, 0.0f);
         dcs.assign((size_t)NDC * BLOCK, 0.0f);
     }
@@ -218,26 +218,43 @@ void cta_step(Engine& e, int rank, int b, const StepArgs& a_rank, uint64_t t, fl
             }
         }
         if (SHAREDW) {
-            // reducer lanes: lane rseg of a row sums slots [rseg * seg_len, (rseg + 1) * seg_len) in order (slots >= BLOCK hold zeros)
-            const int nslots = (int)(hi - lo);
-            for (int row = 0; row < ROWS; ++row)
-                for (int rseg = 0; rseg < lpg; ++rseg) {
-                    const int s0 = rseg * seg_len;
-                    for (int c = 0; c < NDC; ++c) {
-                        float v = acc[((size_t)row * NDC + c) * lpg + rseg];
-                        for (int slot = s0; slot < s0 + seg_len && slot < nslots; ++slot)
-                            v = O::fma(red[(size_t)row * BLOCK + slot], dcs[(size_t)c * BLOCK + slot], v);
-                        acc[((size_t)row * NDC + c) * lpg + rseg] = v;
-                    }
+            // warp-local reduce (persistent.cuh): warp w owns slots [32 w, 32 w + 32).  Pass r0: a row gets S adjacent lanes
+            // (S = 1 in a full pass of 32 rows), lane `sub` sums its 32 / S slots — even slots into accumulator 0, odd slots
+            // into accumulator 1 (the halves of an FFMA2), in slot order — then even + odd and a butterfly over the S lanes.
+            for (int w = 0; w < NW; ++w)
+                for (int r0 = 0; r0 < ROWS; r0 += 32) {
+                    const int nrow = ROWS - r0 < 32 ? ROWS - r0 : 32;
+                    int S = 1;
+                    while (2 * S * nrow <= 32 && 32 / (2 * S) >= 4) S *= 2;  // persist_tail_split(nrow, 4)
+                    const int NSL = 32 / S;
+                    for (int rl = 0; rl < nrow; ++rl)
+                        for (int c = 0; c < NDC; ++c) {
+                            const int row = r0 + rl;
+                            float v[32];
+                            for (int sub = 0; sub < S; ++sub) {
+                                float a2[2] = {0.0f, 0.0f};
+                                for (int q = 0; q < NSL; ++q) {
+                                    const int slot = 32 * w + sub * NSL + q;
+                                    a2[q & 1] = O::fma(red[(size_t)row * BLOCK + slot], dcs[(size_t)c * BLOCK + slot], a2[q & 1]);
+                                }
+                                v[sub] = a2[0] + a2[1];
+                            }
+                            const float cp = butterfly(v, S);
+                            float* pp = &wpart[((size_t)w * ROWS + row) * NDC + c];
+                            *pp = chunk == 0 ? cp : *pp + cp;  // chunks in order
+                        }
                 }
             if (TRACE)
                 for (int64_t i = lo; i < hi; ++i)
                     if (term_flag[(int)(i - lo)]) std::fill(rs.z.begin() + (size_t)i * FA, rs.z.begin() + (size_t)(i + 1) * FA, 0.0f);
         }
     }
-    if (SHAREDW)
-        for (int row = 0; row < ROWS; ++row)
-            for (int c = 0; c < NDC; ++c) part[row * NDC + c] = butterfly(&acc[((size_t)row * NDC + c) * lpg], lpg);
+    if (SHAREDW)  // CTA partial: the warp partials in warp order
+        for (int j = 0; j < ROWS * NDC; ++j) {
+            float acc = wpart[j];
+            for (int w = 1; w < NW; ++w) acc += wpart[(size_t)w * ROWS * NDC + j];
+            part[j] = acc;
+        }
 }
 
 template <int DOM, int BASIS, int P, int AW, int MODE>
@@ -375,7 +392,7 @@ o32_engine_t* o32_engine_create(const rsrl_config_t* cfg, const int32_t* shape, 
     e->F = ipow(cfg->basis_order + 1, e->D); e->FA = e->F * e->AW;
     e->has_trace = algo_has_trace(cfg->algo);
     e->epsilon = cfg->epsilon;
-    if (!pick(cfg->domain, cfg->basis, cfg->basis_order, e->AW, e->sh.mode) || e->sh.lpg > 64 || e->sh.lpr > 64 || e->sh.ncl > 256) { delete e; return nullptr; }
+    if (!pick(cfg->domain, cfg->basis, cfg->basis_order, e->AW, e->sh.mode) || e->sh.lpr > 64 || e->sh.ncl > 256) { delete e; return nullptr; }
     e->ranks.resize(world);
     for (auto& rs : e->ranks) {
         rs.states.assign((size_t)e->N * e->D, 0.0);

@@ -69,7 +69,7 @@ def _i(a):
     return a.ctypes.data_as(_ip)
 
 
-SHAPE_KEYS = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "lpg", "seg_len", "pe_smem"]
+SHAPE_KEYS = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "unused7", "unused8", "pe_smem"]
 
 
 def host_shape(cfg, grid=None, cluster_size=1, block=None, fx=1):
@@ -82,8 +82,8 @@ def host_shape(cfg, grid=None, cluster_size=1, block=None, fx=1):
     trace = cfg.algo in (_abi.SARSA_LAMBDA, _abi.Q_LAMBDA, _abi.TD_LAMBDA)
     N = cfg.n_envs
     if cfg.weight_mode == _abi.PER_ENV:
-        return dict(persistent=1, mode=_abi.PER_ENV, grid=(N + 127) // 128, cluster_size=1, n_clusters=1, block=128, lpr=1, lpg=1,
-                    seg_len=4, pe_smem=1, fx=0)
+        return dict(persistent=1, mode=_abi.PER_ENV, grid=(N + 127) // 128, cluster_size=1, n_clusters=1, block=128, lpr=1, unused7=0,
+                    unused8=0, pe_smem=1, fx=0)
     rows = F * aw if trace else F
     if grid is None:
         g0 = min((N + 127) // 128, 148)
@@ -94,20 +94,12 @@ def host_shape(cfg, grid=None, cluster_size=1, block=None, fx=1):
     per_cta = (N + grid - 1) // grid
     r32 = lambda x: (x + 31) // 32 * 32
     if block is None:
-        block = min(512, max(64, r32(per_cta), r32(rows)))
+        block = min(512, max(64, r32(per_cta), r32(rows)))  # persistent.cuh: kPersistMaxBlock
     lpr = 8
     while rows * lpr > block:
         lpr >>= 1
-    nrg = (rows + 3) // 4
-    lpg = 32
-    while nrg * lpg > block:
-        lpg >>= 1
-    vn = 4
-    seg_len = ((block + lpg - 1) // lpg + vn - 1) // vn * vn
-    if (seg_len // vn) % 2 == 0:
-        seg_len += vn
     return dict(persistent=1, mode=2 if trace else _abi.SHARED, grid=grid, cluster_size=cs, n_clusters=grid // cs, block=block,
-                lpr=lpr, lpg=lpg, seg_len=seg_len, pe_smem=0, fx=fx if cs == 1 else 0)
+                lpr=lpr, unused7=0, unused8=0, pe_smem=0, fx=fx if cs == 1 else 0)
 
 
 class Engine:

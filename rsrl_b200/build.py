@@ -55,9 +55,13 @@ def build(force=False, verbose=False):
     if not force and not _stale(LIB, srcs + hdrs):
         return LIB
     jobs = []
+    # RSRL_BUILD_ONLY=inst_f32_d0,abi (development only): recompile just these objects, trust the others if they exist
+    only = [x for x in os.environ.get("RSRL_BUILD_ONLY", "").split(",") if x]
     for obj, src, defs in _units():
         o, s = os.path.join(OBJ, obj), os.path.join(CSRC, src)
         extra = [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(src, [])]
+        if only and os.path.exists(o) and not any(obj.startswith(x) for x in only):
+            continue
         if force or _stale(o, [s] + hdrs + extra):
             jobs.append([NVCC] + FLAGS + defs + ["-c", s, "-o", o])
 

@@ -217,10 +217,10 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, 1, 1, 1, 1, 4, 0, 0, 0u, 0, 1, 0, 0, nullptr, nullptr};
+    SyncArgs sync = {nullptr, 1, 1, 1, 4, 0, 0, 0u, 0, 1, 0, 0, nullptr, nullptr};
     size_t stage_bytes = 0;
     uint32_t xepoch = 0;  // exchange epoch: counts batched steps over the engine's life, NOT reset by rsrl_engine_reset
-    int pcap = 0;  // padded slot count of the CTA reduce buffers
+    int pcap = 0;  // slot stride of the CTA reduce buffers
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
@@ -286,27 +286,22 @@ static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
     auto round32 = [](int64_t x) { return (int)((x + 31) / 32 * 32); };
     const int64_t per_cta = (e->N + grid - 1) / grid;
     const int64_t rows = e->has_trace ? e->FA : e->F;  // traces: z (F*A rows) lives in shared memory for the whole launch
-    if (e->has_trace && per_cta > 512) return false;   // needs one env per thread
+    if (e->has_trace && per_cta > kPersistMaxBlock) return false;   // needs one env per thread
     int block = round32(per_cta);
     if (block < round32(rows)) block = round32(rows);
     if (block < 64) block = 64;
-    if (block > 512) block = 512;
+    if (block > kPersistMaxBlock) block = kPersistMaxBlock;
     if (block < rows) return false;
-    // persistent.cuh shapes: lpr adjacent lanes own one row in the exchanges between cluster leaders; lpg adjacent lanes own a
-    // group of 4 rows in the CTA reduce, each lane summing one slot segment of seg_len slots.
-    const int vn = (int)(16 / e->rsz);
+    // persistent.cuh shapes: lpr adjacent lanes own one row in the exchanges between cluster leaders; the CTA reduce is warp-local
+    // (its summation order depends on the block size only)
     int lpr = 8;
     while ((int64_t)rows * lpr > block) lpr >>= 1;
-    const int64_t nrg = (rows + 3) / 4;
-    int lpg = 32;
-    while (nrg * lpg > block) lpg >>= 1;
-    int seg_len = ((block + lpg - 1) / lpg + vn - 1) / vn * vn;
-    if ((seg_len / vn) % 2 == 0) seg_len += vn;  // odd number of 16-byte groups: conflict-free segment reads
-    const int cap = lpg * seg_len;
+    const int cap_static = persist_cap_static((int)rows, (int)e->rsz, e->has_trace);
+    const int cap = cap_static ? cap_static : persist_cap(block, (int)e->rsz);
     const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;
     const size_t nvp = (size_t)persist_nvp((int)e->FA, (int)e->rsz);
     const size_t ncl = (size_t)(grid / cs);
-    const size_t elems = (size_t)(2 + cs + (!e->sync.fx && ncl > 1 ? ncl : 0)) * nvp + (size_t)e->F * 4 + (size_t)(nrg * 4 + ndc) * cap;
+    const size_t elems = (size_t)(2 + cs + (!e->sync.fx && ncl > 1 ? ncl : 0)) * nvp + (size_t)e->F * 4 + (size_t)(rows + ndc) * cap + (size_t)kPersistMaxWarps * nvp;
     size_t bytes = 16 + elems * e->rsz;
     if (e->sync.fx) bytes += (size_t)4 * ((e->FA + 1) / 2 * 2) * sizeof(long long);  // running sums of the counting exchange
     if (bytes > 220 * 1024) return false;
@@ -315,7 +310,7 @@ static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
     // spills (~200 B per thread) live in L1, and a larger shared-memory carve-out pushes them out to L2 (measured: +27 % step time).
     if (grid > 1 && block <= 256 && bytes < 116 * 1024) bytes = 116 * 1024;
     e->pcap = cap;
-    e->sync.lpr = lpr; e->sync.lpg = lpg; e->sync.seg_len = seg_len;
+    e->sync.lpr = lpr; e->sync.cap = cap;
     e->sync.cluster_size = cs; e->sync.n_clusters = grid / cs;
     e->pgrid = grid; e->pblock = block; e->psmem = bytes;
     return true;
@@ -345,8 +340,8 @@ static void choose_persistent(rsrl_engine* e) {
     if (g0 > sms) g0 = sms;
     // fp32: the counting exchange (persistent.cuh), one L2 hop, no clusters: all SMs take part.  f64 engines: cluster + LL-line exchange.
     e->sync.fx = e->cfg.dtype == RSRL_F32 ? 1 : 0;
-    e->sync.nsub = getenv("RSRL_B200_NSUB") ? atoi(getenv("RSRL_B200_NSUB")) : 1;  // sub-tables (measured: more tables = more polls = slower)
-    if (e->sync.nsub != 1 && e->sync.nsub != 2 && e->sync.nsub != 4) e->sync.nsub = 1;
+    e->sync.ngroups = getenv("RSRL_B200_NGROUPS") ? atoi(getenv("RSRL_B200_NGROUPS")) : kMaxGroups;  // multi-GPU: CTA groups per GPU
+    if (e->sync.ngroups < 1 || e->sync.ngroups > kMaxGroups) e->sync.ngroups = kMaxGroups;
     // first poll 400 ns after the reductions were issued: earlier polls only queue in front of them in L2 (measured, profiles/r02_persistent.md)
     e->sync.poll_delay_ns = getenv("RSRL_B200_POLL_DELAY") ? atoi(getenv("RSRL_B200_POLL_DELAY")) : 400;
     e->sync.poll_backoff_ns = getenv("RSRL_B200_POLL_BACKOFF") ? atoi(getenv("RSRL_B200_POLL_BACKOFF")) : 0;
@@ -504,7 +499,7 @@ int rsrl_engine_destroy(rsrl_engine_t* e) {
         cudaMemcpy(h.data(), e->phase_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         const char* names_d[8] = {"dW: inputs -> u, v (regs)", "dW: wait MMA (buffer free)", "dW: split + scalar stores", "dW: fence + __syncthreads",
                                   "dW: MMA issue (thread 0)", "-", "-", "-"};
-        const char* names_p[8] = {"env compute", "wait CTA (bar 1)", "CTA reduce (+bar)", "exchange: rest (member: all)", "final bar",
+        const char* names_p[8] = {"env compute (warp 0)", "warp reduce + CTA barrier", "warp partials -> CTA partial", "exchange", "final bar",
                                   "leader: wait members (hop A)", "leader: sum + hops N/B", "-"};
         const char* names_t[8] = {"load + tables", "unit compute (regs)", "wait MMA (mbarrier)", "contract (LDTM + FMA)", "store unit + sync + issue",
                                   "TD + stores + bookkeeping", "issuer: MMA issue (pipe busy)", "issuer: idle (no unit ready)"};
@@ -657,10 +652,10 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
         e->inbox_bytes = (size_t)2 * kMaxRanks * e->sync.n_clusters * e->FA * (e->rsz / 4) * sizeof(uint2);
         if (e->sync.fx) {  // counting exchange: local table, running sums, and the world table in the peer-visible mailbox
             const size_t tab = (size_t)2 * e->FA * kAccStride * sizeof(unsigned long long);
-            E_TRY(cudaMalloc(&e->sync.acc, tab * e->sync.nsub));
-            E_TRY(cudaMemset(e->sync.acc, 0, tab * e->sync.nsub));
-            E_TRY(cudaMalloc(&e->sync.prev, (size_t)4 * e->FA * sizeof(long long)));
-            E_TRY(cudaMemset(e->sync.prev, 0, (size_t)4 * e->FA * sizeof(long long)));
+            E_TRY(cudaMalloc(&e->sync.acc, tab * kMaxGroups));
+            E_TRY(cudaMemset(e->sync.acc, 0, tab * kMaxGroups));
+            E_TRY(cudaMalloc(&e->sync.prev, (size_t)(2 + 2 * kMaxGroups) * e->FA * sizeof(long long)));
+            E_TRY(cudaMemset(e->sync.prev, 0, (size_t)(2 + 2 * kMaxGroups) * e->FA * sizeof(long long)));
             e->inbox_bytes = tab;
         }
         E_TRY(cudaMalloc(&e->inbox, e->inbox_bytes));
@@ -1096,7 +1091,7 @@ int rsrl_engine_get_launch_shape(rsrl_engine_t* e, int32_t out[24]) {
     if (!e || !out) return fail(RSRL_EINVAL, "null argument");
     memset(out, 0, 24 * sizeof(int32_t));
     out[0] = e->persistent ? 1 : 0; out[1] = e->pmode; out[2] = e->pgrid; out[3] = e->sync.cluster_size; out[4] = e->sync.n_clusters;
-    out[5] = e->pblock; out[6] = e->sync.lpr; out[7] = e->sync.lpg; out[8] = e->sync.seg_len; out[9] = e->sync.pe_smem;
+    out[5] = e->pblock; out[6] = e->sync.lpr; out[7] = 0; out[8] = 0;  /* (the CTA reduce is warp-local: its order depends on the block size only) */ out[9] = e->sync.pe_smem;
     out[10] = e->world; out[11] = e->rank; out[12] = e->peers_attached ? 1 : 0; out[13] = (int32_t)e->psmem;
     out[14] = e->tile ? 1 : 0; out[15] = e->f4 ? (1 + e->f4tc) : 0; out[16] = e->sync.fx;
     return RSRL_OK;
@@ -1170,6 +1165,7 @@ int rsrl_engine_peer_export(rsrl_engine_t* e, uint8_t handle_out[64]) {
 
 int rsrl_engine_peer_attach(rsrl_engine_t* e, const uint8_t* handles, int rank, int world) {
     if (!e || !handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(RSRL_EINVAL, "bad argument (world <= 8)");
+    if (e->xepoch != 0) return fail(RSRL_EINVAL, "attach the peers before the first step (the exchange tables count arrivals from step 0)");
     if (!e->inbox) return fail(RSRL_EINVAL, "engine has no peer mailbox (SHARED weights + persistent kernel only)");
     CU_TRY(cudaSetDevice(e->cfg.device));
     for (int r = 0; r < world; ++r) {

@@ -18,7 +18,11 @@ namespace rsrl {
 // f64 physics: explicit round-to-nearest ops (hostdev.h: dmul / dadd / dsub / ddiv) so that nvcc does not contract a*b+c
 // into DFMA — the reference (Rust, no FMA contraction) rounds after every operation.
 // clip!(lb, x, ub) = lb.max(ub.min(x))  (rsrl_domains/src/macros.rs:20-24); fmin/fmax drop NaN like Rust
-__host__ __device__ __forceinline__ double dclip(double lb, double x, double ub) { return fmax(lb, fmin(ub, x)); }
+// as two compare-selects: the same values as fmax(lb, fmin(ub, x)) for lb < ub, neither zero (NaN -> ub), half the instructions
+__host__ __device__ __forceinline__ double dclip(double lb, double x, double ub) {
+    const double t = x < ub ? x : ub;
+    return t > lb ? t : lb;
+}
 // wrap!(lb, x, ub)  (macros.rs:3-18)
 __host__ __device__ __forceinline__ double dwrap(double lb, double x, double ub) {
     double nx = x;
@@ -406,6 +410,37 @@ struct GridBasis {
     template <class Fn>
     __host__ __device__ __forceinline__ static void for_each(const Tab& t, Fn f) {
         using O = RealOps<R>;
+#ifdef __CUDA_ARCH__
+        if constexpr (D == 2 && BASIS == RSRL_FOURIER && sizeof(R) == 4) {
+            // fp32 on the device: two features per issue slot (FMUL2 + FFMA2 with the dimension-0 entry broadcast from a scalar
+            // register).  Per feature the operations are those of the scalar form below — (-s0) * s1 == -(s0 * s1) exactly —
+            // so the host build (oracle32) keeps the scalar form.
+#pragma unroll
+            for (int i0 = 0; i0 < N1; ++i0) {
+                const int c0 = P - i0;
+                if (c0 == 0) {
+#pragma unroll
+                    for (int i1 = 0; i1 < N1; ++i1) f(i0 * N1 + i1, i1 == P ? (R)1 : t.c[1][P - i1 - 1]);
+                } else {
+                    const float ca = t.c[0][c0 - 1], nsa = -t.s[0][c0 - 1];
+#pragma unroll
+                    for (int i1 = 0; i1 < P; i1 += 2) {
+                        const int c1 = P - i1;
+                        if (c1 >= 2) {
+                            const float2 m = __fmul2_rn(make_float2(nsa, nsa), make_float2(t.s[1][c1 - 1], t.s[1][c1 - 2]));
+                            const float2 ph = __ffma2_rn(make_float2(ca, ca), make_float2(t.c[1][c1 - 1], t.c[1][c1 - 2]), m);
+                            f(i0 * N1 + i1, ph.x);
+                            f(i0 * N1 + i1 + 1, ph.y);
+                        } else {
+                            f(i0 * N1 + i1, ffma(ca, t.c[1][0], fmul(nsa, t.s[1][0])));
+                        }
+                    }
+                    f(i0 * N1 + P, ca);
+                }
+            }
+            return;
+        }
+#endif
         if (D == 2) {
 #pragma unroll
             for (int i0 = 0; i0 < N1; ++i0) {

@@ -37,6 +37,7 @@
 // One DSMEM hop costs ~250 cycles, one L2 LL hop ~700 (tools/microbench/pingpong.cu); round 1's version
 // (two L2 hops polled by all 148 CTAs, NVLink hop serialised behind CTA 0) is in profiles/r01_final.md.
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace rsrl {
@@ -45,27 +46,30 @@ constexpr int kModeSharedTrace = 2;  // internal MODE: SHARED weights + per-env 
 constexpr int kMaxRanks = 8;
 constexpr int kMaxClusters = 64;     // leaders that exchange through L2
 constexpr int kMaxClusterSize = 16;
+constexpr int kMaxGroups = 8;        // group tables of the multi-GPU counting exchange
 constexpr int kAccStride = 16;       // 64-bit words between two accumulators: one 128-byte line each (atomics on one line serialise)
 constexpr double kFxScale = 1099511627776.0;   // 2^40: fixed-point unit of the counting exchange
 constexpr float kFxLimit = 16384.0f;           // |CTA partial| must stay below 2^14 (2^54 in fixed point; the field has 56 bits)
+
+// two fused multiply-adds per issue slot (FFMA2, sm_100): each half is an ordinary IEEE fma, so the host replay stays scalar
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 struct SyncArgs {
     uint4* stage;   // [2][n_clusters][ROWS * LPW]   (world-)cluster partial rows (parity double-buffered)
     int cluster_size;
     int n_clusters;
     int lpr;        // LL lanes per row (power of two <= 8, ROWS * lpr <= blockDim)
-    int lpg;        // reducer lanes per group of 4 rows (power of two <= 32, ceil(ROWS / 4) * lpg <= blockDim)
-    int seg_len;    // slots per reducer lane (odd multiple of the 16-byte vector width); row stride cap = lpg * seg_len
+    int cap;        // slot stride of the reduce rows when it is not a compile-time constant (persist_cap_static == 0): persist_cap(blockDim)
     int pe_smem;    // PER_ENV: keep every env's own W (F*A values, column `tid`) in shared memory for the whole launch
     int debug_skip; // development timing aid (RSRL_B200_DEBUG_SKIP): bit 0 skips the grid exchange, bit 1 the CTA reduce (wrong results)
     uint32_t epoch_base;  // exchange epoch before the launch's first step (monotonic over the engine's life, never reset)
     // fp32 exchange through counting accumulators in L2 (see the header comment); fx == 0: the cluster + LL-line exchange
     int fx;
-    int nsub;                 // sub-tables per parity (1, 2 or 4)
+    int ngroups;              // several GPUs: CTA groups per GPU (<= kMaxGroups), each with its own table and a leader that forwards its total
     int poll_delay_ns;        // pause between the reductions and the first poll / between two polls: polls that come before the last
     int poll_backoff_ns;      // partial has landed only queue in front of the reductions in L2
-    unsigned long long* acc;  // [2][nsub][NV][kAccStride] running fixed-point sums of the CTA partials + arrival count in the low byte (parity double-buffered)
-    long long* prev;          // [4][NV] running sums at the previous completion: acc parity 0, 1, world table parity 0, 1 (written at kernel end)
+    unsigned long long* acc;  // [2][kMaxGroups][NV][kAccStride] running fixed-point sums of the CTA partials + arrival count in the low byte (parity double-buffered)
+    long long* prev;          // [2 + 2 * kMaxGroups][NV] running sums at the previous completion: world table parity 0, 1, then every group table
 };
 
 // Cross-GPU exchange (one process per GPU): every rank owns an inbox of 8-byte LL words
@@ -241,14 +245,46 @@ __device__ __forceinline__ void row_butterfly(R* v, int lpr) {
 template <typename R> struct Vec16;  // 16-byte shared-memory vector of R
 template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
+// acc[0] += p.even * d.even, acc[1] += p.odd * d.odd over the slots of one 16-byte group, in slot order
+__device__ __forceinline__ void pair_fma(const float4& p, const float4& d, float* acc) {
+    float2 a = make_float2(acc[0], acc[1]);
+    a = ffma2(make_float2(p.x, p.y), make_float2(d.x, d.y), a);
+    a = ffma2(make_float2(p.z, p.w), make_float2(d.z, d.w), a);
+    acc[0] = a.x; acc[1] = a.y;
+}
+__device__ __forceinline__ void pair_fma(const double2& p, const double2& d, double* acc) {
+    acc[0] = dfma(p.x, d.x, acc[0]);
+    acc[1] = dfma(p.y, d.y, acc[1]);
+}
 __device__ __forceinline__ float vget(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 __device__ __forceinline__ double vget(const double2& v, int i) { return i == 0 ? v.x : v.y; }
+
+// CTA reduce: WARP-LOCAL.  Each warp reduces the 32 slots of its own envs right after it has stepped them — no CTA barrier
+// between the env phase and the reduce, no idle warps, and a slow warp's env phase overlaps the other warps' reduces.
+// Pass p: lane l owns row 32 p + l and sums the warp's 32 slots (16-byte loads; even / odd slots in the two halves of an
+// FFMA2).  The row stride `cap` is 4 (mod 32) words, so the 32 rows of a pass fall into distinct bank groups.  A last pass
+// with n < 32 rows gives every row S = persist_tail_split(n) adjacent lanes (32 / S slots each, butterfly over the S lanes).
+// The warp partials go to wpart[warp][NV]; after one CTA barrier thread j adds wpart[0..NW)[j] in warp order.
+constexpr int kPersistMaxBlock = 512;  // (the register file is per scheduler: 13-16 warps all mean 4 warps on one scheduler = 128 registers)
+constexpr int kPersistMaxWarps = kPersistMaxBlock / 32;
+__host__ __device__ constexpr int persist_tail_split(int nrow, int vn) {  // lanes per row in a pass of nrow <= 32 rows; vn = slots per 16 bytes
+    int s = 1;
+    while (2 * s * nrow <= 32 && 32 / (2 * s) >= vn) s *= 2;
+    return s;
+}
+// Row stride of the reduce buffer in slots: >= block, a multiple of the 16-byte vector, 4 (mod 32) words.
+__host__ __device__ constexpr int persist_cap(int block, int rsz) { return block + 16 / rsz; }
+// A compile-time stride whenever the rows fit (every STS / LDS of the env phase gets an immediate offset instead of an address
+// computation: -70 instructions per env-step on Fourier(5)); otherwise persist_cap(blockDim) at run time.
+__host__ __device__ constexpr int persist_cap_static(int rows, int rsz, bool trace) {
+    return (!trace && (long long)rows * persist_cap(kPersistMaxBlock, rsz) * rsz <= 160 * 1024) ? persist_cap(kPersistMaxBlock, rsz) : 0;
+}
 
 // NV values of R padded to a multiple of 16 bytes (bulk copies); host and device lay the shared memory out from this
 __host__ __device__ constexpr int persist_nvp(int nv, int rsz) { return (nv * rsz + 15) / 16 * 16 / rsz; }
 
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE>
-__global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
+__global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock, MODE == RSRL_PER_ENV ? 4 : 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     using O = RealOps<R>;
@@ -265,7 +301,6 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     constexpr uint32_t NVB = NVP * sizeof(R);               // bytes of one partial (multiple of 16)
     constexpr int NCH = (int)(NVB / 16);                    // 16-byte chunks of one partial (one st.async each)
     constexpr bool FX = sizeof(R) == 4;                     // fp32: counting exchange; f64: cluster + LL lines (each instantiation carries one)
-    constexpr int MAXSUB = 4;                               // sub-tables of the counting exchange (CTA b adds to sub-table b % nsub)
     constexpr int NVP8 = (NV + 1) / 2 * 2;                  // prevs rows (long long), padded to 16 bytes
     constexpr int WS = 4;            // padded row stride of the shared W copy: one LDS.128 per feature row
     constexpr int FApad = F * WS;
@@ -280,36 +315,41 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     const int64_t end = base + per_cta < N ? base + per_cta : N;
     const int n_chunks = (int)((per_cta + BLOCK - 1) / BLOCK);
     const bool resident = n_chunks == 1;  // one env per thread: state stays in registers across steps
-    const int lpr = sy.lpr, lpg = sy.lpg, seg_len = sy.seg_len, cap = lpg * seg_len;
-    constexpr int RPT = 4;                      // rows per reducer thread: one dcs load feeds RPT rows
-    constexpr int ROWSP = (ROWS + RPT - 1) / RPT * RPT;
+    constexpr int CAPT = SHAREDW ? persist_cap_static(ROWS, (int)sizeof(R), TRACE) : 0;
+    const int lpr = sy.lpr, cap = CAPT ? CAPT : sy.cap;
+    constexpr bool ALIAS_TAB = SHAREDW && !TRACE;  // phi(s_t) is in shared memory after evalS: the tables of s' may overwrite those of s
     const int CS = SHAREDW ? sy.cluster_size : 1;
     const int crank = CS > 1 ? (int)cl_ctarank() : 0;   // rank in the cluster; rank 0 leads
     const int cid = b / CS;                             // cluster index
     const bool leader = crank == 0;
 
-    // shared memory (SHARED modes).  Row stride cap = lpg * seg_len with seg_len / V::N odd: the lpg lanes
-    // of a row group read 16-byte groups seg * seg_len + slot that fall into distinct bank groups.  Slots
-    // >= BLOCK are zero and stay zero.
+    // shared memory (SHARED modes).  Row stride cap > BLOCK slots (persist_cap); slots >= BLOCK are never read.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* mbars = reinterpret_cast<unsigned long long*>(smem_raw);  // [0] leader: members' partials, [1] member: the total
     R* part = reinterpret_cast<R*>(smem_raw + 16);  // [NVP]     this CTA's dW partial (bulk-copy source)
     R* totbuf = part + NVP;                         // [NVP]     grid total (leader: bulk-copy source, member: destination)
     R* inbuf = totbuf + NVP;                        // [CS][NVP] leader: the members' partials; slot 0: the grid total (bulk-copy source)
     R* Wsm = inbuf + (size_t)CS * NVP;        // [FApad]
-    R* red = Wsm + FApad;                     // [ROWSP][cap] phi(s_t) feature-major, or the traces z[F*A][slot]
-    R* dcs = red + (size_t)ROWSP * cap;       // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
-    R* gath = dcs + (size_t)NDC * cap;        // [n_clusters][NVP] leader: the clusters' partials gathered from L2 (only when n_clusters > 1)
+    R* red = Wsm + FApad;                     // [ROWS][cap]  phi(s_t) feature-major, or the traces z[F*A][slot]
+    R* dcs = red + (size_t)ROWS * cap;        // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
+    R* wpart = dcs + (size_t)NDC * cap;       // [kPersistMaxWarps][NVP] warp partials of the CTA reduce
+    R* gath = wpart + (size_t)kPersistMaxWarps * NVP;  // [n_clusters][NVP] leader: the clusters' partials gathered from L2 (only when n_clusters > 1)
     // counting exchange: running sums seen at the previous completion [4][NVP8] (local parity 0, 1; world parity 0, 1); it takes gath's place
     long long* prevs = reinterpret_cast<long long*>(gath);
     const uint32_t mb_in = cl_smem_u32(&mbars[0]), mb_tot = cl_smem_u32(&mbars[1]);
 
     if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
-        for (int j = tid; j < (ROWSP + NDC) * cap; j += BLOCK) red[j] = (R)0;
+        for (int j = tid; j < (ROWS + NDC) * cap + kPersistMaxWarps * NVP; j += BLOCK) red[j] = (R)0;
         for (int j = tid; j < NVP; j += BLOCK) { part[j] = (R)0; totbuf[j] = (R)0; }
         if (FX) {
-            for (int j = tid; j < 4 * NV; j += BLOCK) prevs[(j / NV) * NVP8 + j % NV] = sy.prev[j];
+            // running sums at the previous completion: rows 0, 1 = the table this CTA polls (one GPU: the only table; several GPUs:
+            // the table of the group it leads), rows 2, 3 = the world table.  sy.prev: [2][NV] world, then [kMaxGroups][2][NV] groups.
+            const int myg = (pe.world > 1 && b < kMaxGroups) ? b : 0;
+            for (int j = tid; j < 2 * NV; j += BLOCK) {
+                prevs[(j / NV) * NVP8 + j % NV] = sy.prev[(size_t)(2 + 2 * myg) * NV + j];
+                prevs[(2 + j / NV) * NVP8 + j % NV] = sy.prev[j];
+            }
         }
         if (CS > 1) {
             if (tid == 0) {
@@ -347,10 +387,6 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     typename GB::Tab tab_s, tab_n;
     bool have_tab = false;  // tab_s holds the tables of s (carried from the previous step's s')
 
-    // reducers: lanes [rg * lpg, (rg + 1) * lpg) own rows 4 rg .. 4 rg + 3; lane `rseg` sums slot segment rseg
-    const int rg = tid / lpg, rseg = tid % lpg;
-    const bool reducer = SHAREDW && rg < ROWSP / RPT;
-    const bool warp_red = SHAREDW && (tid & ~31) < (ROWSP / RPT) * lpg;  // warp-uniform
     // LL row ownership: lanes [row * lpr, (row + 1) * lpr) own row `row` in the exchanges between leaders
     const int row = tid / lpr, rl = tid % lpr;
     const bool row_valid = SHAREDW && row < ROWS;
@@ -367,12 +403,6 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
         if (prof) c0 = clock64();
-        R racc[RPT][NDC];
-#pragma unroll
-        for (int r = 0; r < RPT; ++r)
-#pragma unroll
-            for (int c = 0; c < NDC; ++c) racc[r][c] = (R)0;
-
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             if (!resident) {
                 i = base + (int64_t)chunk * BLOCK + tid;
@@ -408,29 +438,43 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                         for (int c = 0; c < AW; ++c) w[c] = Wg[(int64_t)(k * AW + c) * N + i];
                     }
                 };
-                auto evalS = [&](const typename GB::Tab& tab, R* q) {  // Q(s_t) and, SHARED, the phi(s_t) row
+                // fp32, SHARED: q[0..1] += phi * W[k][0..1] is ONE FFMA2 (phi broadcast from a scalar register, the W pair straight
+                // from the LDS.128) — per component the same fma as the scalar form, so oracle32 replays it unchanged
+                constexpr bool PACKQ = sizeof(R) == 4 && SHAREDW && AW >= 2 && AW <= 4;
+                auto eval = [&](const typename GB::Tab& tab, R* q, auto rec) {
+                    if constexpr (PACKQ) {
+                        // (without this the compiler keeps the 108 W values of the first evaluation alive for the second one: 600 bytes
+                        // of local-memory spills per thread instead of 36 LDS.128)
+                        asm volatile("" ::: "memory");
+                        float2 q01 = make_float2(0.0f, 0.0f), q23 = make_float2(0.0f, 0.0f);
+                        float q2 = 0.0f;
+                        GB::for_each(tab, [&](int k, R phi) {
+                            if (decltype(rec)::value) red[k * cap + tid] = phi;
+                            const float4 w = *reinterpret_cast<const float4*>(Wsm + k * WS);
+                            q01 = ffma2(make_float2(phi, phi), make_float2(w.x, w.y), q01);
+                            if (AW == 3) q2 = ffma(phi, w.z, q2);
+                            if (AW == 4) q23 = ffma2(make_float2(phi, phi), make_float2(w.z, w.w), q23);
+                        });
+                        q[0] = q01.x; q[1] = q01.y;
+                        if (AW == 3) q[2] = q2;
+                        if (AW == 4) { q[2] = q23.x; q[3] = q23.y; }
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < AW; ++c) q[c] = (R)0;
-                    GB::for_each(tab, [&](int k, R phi) {
-                        if (SHAREDW && !TRACE) red[k * cap + tid] = phi;
-                        R w[AW];
-                        wrow(k, w);
+                        for (int c = 0; c < AW; ++c) q[c] = (R)0;
+                        GB::for_each(tab, [&](int k, R phi) {
+                            if (decltype(rec)::value) red[k * cap + tid] = phi;
+                            R w[AW];
+                            wrow(k, w);
 #pragma unroll
-                        for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, w[c], q[c]);
-                    });
+                            for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, w[c], q[c]);
+                        });
+                    }
                 };
-                auto evalN = [&](const typename GB::Tab& tab, R* q) {
-#pragma unroll
-                    for (int c = 0; c < AW; ++c) q[c] = (R)0;
-                    GB::for_each(tab, [&](int k, R phi) {
-                        R w[AW];
-                        wrow(k, w);
-#pragma unroll
-                        for (int c = 0; c < AW; ++c) q[c] = O::mac(phi, w[c], q[c]);
-                    });
-                };
+                // Q(s_t) and, SHARED without traces, the phi(s_t) row; Q(s')
+                auto evalS = [&](const typename GB::Tab& tab, R* q) { eval(tab, q, std::integral_constant<bool, SHAREDW && !TRACE>()); };
+                auto evalN = [&](const typename GB::Tab& tab, R* q) { eval(tab, q, std::integral_constant<bool, false>()); };
                 auto prep = [](const double* st, typename GB::Tab& tb) { grid_prepare<R, Dom, P, BASIS>(st, tb); };
-                env_core<R, DOM, AW, false>(a, t, g, s, prep, evalS, evalN, tab_s, tab_n, have_tab, o, 0, 0.0, false, nullptr);
+                env_core<R, DOM, AW, false>(a, t, g, s, prep, evalS, evalN, tab_s, ALIAS_TAB ? tab_s : tab_n, have_tab, o, 0, 0.0, false, nullptr);
                 if (a.td) static_cast<R*>(a.td)[i] = o.residual;
                 if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
                 if (MODE == RSRL_PER_ENV) {
@@ -463,7 +507,7 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                 ep = env_bookkeeping<Dom>(a, t, i, g, s, ep, o.terminated, &was_reset);
                 act = o.act;
                 have_tab = resident && !was_reset;  // s_{t+1} = s': reuse its tables
-                if (have_tab) tab_s = tab_n;
+                if (have_tab && !ALIAS_TAB) tab_s = tab_n;
                 if (!resident) {
                     a.ep_steps[i] = ep;
                     a.actions[i] = act;
@@ -480,28 +524,49 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
                     for (int c = 0; c < AW; ++c) dcs[c * cap + tid] = (active && (TDPRED || c == o.act)) ? o.coef : (R)0;
                 }
                 // (a slot idle in this chunk keeps a stale but finite row; its dcs entries are 0)
-                __syncthreads();
-                if (prof) tick(1);
-                if (reducer && !(sy.debug_skip & 2)) {
-                    const int s0 = rseg * seg_len;
-                    const R* prow = red + (size_t)(rg * RPT) * cap + s0;
-                    const R* drow = dcs + s0;
-                    for (int slot = 0; slot < seg_len; slot += V::N) {
-                        vec_t dv[NDC];
+                __syncwarp();
+                // ---- warp-local reduce of this warp's 32 slots (see the header) ----
+                if (!(sy.debug_skip & 2)) {
+                    const int lane = tid & 31, slot0 = tid & ~31;
+                    R* wp = wpart + (size_t)(tid >> 5) * NVP;
 #pragma unroll
-                        for (int c = 0; c < NDC; ++c) dv[c] = *reinterpret_cast<const vec_t*>(drow + (size_t)c * cap + slot);
+                    for (int r0 = 0; r0 < ROWS; r0 += 32) {
+                        constexpr int VN = V::N;
+                        const int nrow = ROWS - r0 < 32 ? ROWS - r0 : 32;          // compile-time after unrolling
+                        const int S = persist_tail_split(nrow, VN), NSL = 32 / S;  // lanes per row, slots per lane
+                        const int rloc = lane / S, sub = lane % S;
+                        R acc[NDC][2];
 #pragma unroll
-                        for (int r = 0; r < RPT; ++r) {
-                            const vec_t pv = *reinterpret_cast<const vec_t*>(prow + (size_t)r * cap + slot);
+                        for (int c = 0; c < NDC; ++c) acc[c][0] = acc[c][1] = (R)0;
+                        if (rloc < nrow) {
+                            const R* prow = red + (size_t)(r0 + rloc) * cap + slot0 + sub * NSL;
+                            const R* drow = dcs + slot0 + sub * NSL;
 #pragma unroll
-                            for (int u = 0; u < V::N; ++u) {
+                            for (int gq = 0; gq < NSL / VN; ++gq) {
+                                const vec_t pv = *reinterpret_cast<const vec_t*>(prow + gq * VN);
 #pragma unroll
-                                for (int c = 0; c < NDC; ++c) racc[r][c] = O::fma(vget(pv, u), vget(dv[c], u), racc[r][c]);
+                                for (int c = 0; c < NDC; ++c)
+                                    pair_fma(pv, *reinterpret_cast<const vec_t*>(drow + (size_t)c * cap + gq * VN), acc[c]);
+                            }
+                        }
+                        R v[NDC];
+#pragma unroll
+                        for (int c = 0; c < NDC; ++c) v[c] = acc[c][0] + acc[c][1];
+#pragma unroll
+                        for (int off = 1; off < S; off <<= 1) {
+#pragma unroll
+                            for (int c = 0; c < NDC; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], off);
+                        }
+                        if (rloc < nrow && sub == 0) {
+#pragma unroll
+                            for (int c = 0; c < NDC; ++c) {
+                                R* pp = wp + (r0 + rloc) * NDC + c;
+                                *pp = chunk == 0 ? v[c] : *pp + v[c];  // chunks in order
                             }
                         }
                     }
                 }
-                if (n_chunks > 1 || TRACE) __syncthreads();  // rows are rewritten by the next chunk / cleared below
+                if (n_chunks > 1 || TRACE) __syncwarp();  // the warp's rows are rewritten by the next chunk / cleared below
                 if (TRACE && active && o.terminated) {  // trace.reset() (sarsa_lambda.rs:78, q_lambda.rs:81, td_lambda.rs:61)
                     for (int j = 0; j < FA; ++j) red[(size_t)j * cap + tid] = (R)0;
                 }
@@ -509,23 +574,20 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
         }
 
         if (SHAREDW) {
-            // CTA partial: butterfly over the lpg lanes of each row group, lane 0 writes the rows to `part`
-            if (warp_red) {
-                for (int off = 1; off < lpg; off <<= 1) {
-#pragma unroll
-                    for (int r = 0; r < RPT; ++r)
-#pragma unroll
-                        for (int c = 0; c < NDC; ++c) racc[r][c] += __shfl_xor_sync(0xffffffffu, racc[r][c], off);
-                }
-                if (reducer && rseg == 0) {
-#pragma unroll
-                    for (int r = 0; r < RPT; ++r)
-#pragma unroll
-                        for (int c = 0; c < NDC; ++c)
-                            if (rg * RPT + r < ROWS) part[(rg * RPT + r) * NDC + c] = racc[r][c];
-                }
-            }
             __syncthreads();
+            if (prof) tick(1);
+            // CTA partial: the warp partials added in warp order (thread j owns value j)
+            const int NW = BLOCK >> 5;
+            for (int j = tid; j < NV; j += BLOCK) {
+                R v[kPersistMaxWarps];  // all loads first (rows of warps >= NW hold zeros): one shared-memory latency, not NW
+#pragma unroll
+                for (int w = 0; w < kPersistMaxWarps; ++w) v[w] = wpart[(size_t)w * NVP + j];
+                R acc = v[0];
+#pragma unroll
+                for (int w = 1; w < kPersistMaxWarps; ++w) if (w < NW) acc += v[w];
+                part[j] = acc;
+            }
+            if (!FX) __syncthreads();  // fp32: thread j alone reads part[j] below (reduction, poll, W update): no barrier
             if (prof) tick(2);
             const uint32_t epoch = sy.epoch_base + (uint32_t)step + 1u;
             const int par = (int)(epoch & 1u);
@@ -533,56 +595,56 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
             const R* total = part;                     // one CTA (or exchange skipped): its partial is the total
             if constexpr (FX) {
               if ((G > 1 || pe.world > 1) && !(sy.debug_skip & 1)) {
-                // ---- counting accumulators (fp32): one L2 hop ----
+                // ---- counting accumulators (fp32) ----
+                // One GPU: every CTA adds to ONE table and every CTA polls it (one L2 hop).
+                // Several GPUs: the CTAs form NG groups (CTA b belongs to group b % NG, CTA q < NG leads group q); a group's table
+                // fills quickly (G / NG reductions per word), its leader forwards the group total to the world table of EVERY GPU
+                // through the NVLink peer pointers, and every CTA polls its own GPU's world table (world * NG arrivals per step).
+                // The NVLink flight of the early groups overlaps the local reductions of the late ones; nothing waits for a
+                // whole-GPU total.  Integer sums: the result does not depend on the grouping.
                 const int p = par;
                 const unsigned long long k = ((unsigned long long)epoch + (unsigned long long)p) >> 1;  // steps of this parity so far, this one included
                 const bool multi = pe.world > 1;
-                const int nsub = sy.nsub;  // CTA b adds into sub-table b % nsub: fewer same-address reductions queue up in L2
-                unsigned long long* accp = sy.acc + (size_t)p * nsub * NV * kAccStride;
-                {
-                    unsigned long long* mine = accp + (size_t)(b % nsub) * NV * kAccStride;
-                    for (int j = tid; j < NV; j += BLOCK) {
-                        float x = (float)part[j];
-                        if (!(fabsf(x) < kFxLimit)) { atomicExch(&a.counters->nonfinite, 1); x = 0.0f; }  // NaN / Inf / beyond the fixed-point range
-                        red_add_u64_gpu(mine + (size_t)j * kAccStride, ((unsigned long long)fx_from_float(x) << 8) + 1ull);
-                    }
+                constexpr int AST = kAccStride;  // one 128-byte line per accumulator: packed words or one bulk reduction
+                                                 // (cp.reduce.async.bulk.add.u64) per CTA are slower (profiles/r02_persistent.md)
+                const int NG = multi ? (sy.ngroups < G ? sy.ngroups : G) : 1;
+                const int grp = b % NG;
+                unsigned long long* gtab = sy.acc + ((size_t)p * kMaxGroups + grp) * NV * AST;  // my group's table
+                for (int j = tid; j < NV; j += BLOCK) {
+                    float x = (float)part[j];
+                    if (!(fabsf(x) < kFxLimit)) { atomicExch(&a.counters->nonfinite, 1); x = 0.0f; }  // NaN / Inf / beyond the fixed-point range
+                    red_add_u64_gpu(gtab + (size_t)j * AST, ((unsigned long long)fx_from_float(x) << 8) + 1ull);
                 }
-                if (sy.poll_delay_ns > 0) __nanosleep((unsigned)sy.poll_delay_ns);
-                if (!multi || b == 0) {
+                if (sy.poll_delay_ns > 0 && !multi) __nanosleep((unsigned)sy.poll_delay_ns);
+                if (!multi || b < NG) {
+                    const unsigned long long cnt = (unsigned long long)((G - grp + NG - 1) / NG) * k;  // CTAs grp, grp + NG, ... over k steps
                     for (int j = tid; j < NV; j += BLOCK) {
-                        unsigned long long w[MAXSUB];
-#pragma unroll
-                        for (int q = 0; q < MAXSUB; ++q)
-                            if (q < nsub) w[q] = ld_u64_gpu(accp + ((size_t)q * NV + j) * kAccStride);
-                        long long sum = 0;
-#pragma unroll
-                        for (int q = 0; q < MAXSUB; ++q) {
-                            if (q < nsub) {
-                                const unsigned long long cnt = (unsigned long long)((G - q + nsub - 1) / nsub) * k;  // CTAs q, q + nsub, ... over k steps
-                                const unsigned long long* word = accp + ((size_t)q * NV + j) * kAccStride;
-                                while ((w[q] & 0xFFull) != (cnt & 0xFFull)) {
-                                    if (sy.poll_backoff_ns > 0) __nanosleep((unsigned)sy.poll_backoff_ns);
-                                    w[q] = ld_u64_gpu(word);
-                                }
-                                sum += fx_running_sum(w[q], cnt);
-                            }
+                        const unsigned long long* word = gtab + (size_t)j * AST;
+                        unsigned long long w = ld_u64_gpu(word);
+                        while ((w & 0xFFull) != (cnt & 0xFFull)) {
+                            if (sy.poll_backoff_ns > 0) __nanosleep((unsigned)sy.poll_backoff_ns);
+                            w = ld_u64_gpu(word);
                         }
+                        const long long sum = fx_running_sum(w, cnt);
                         const long long dq = fx_sext56(sum - prevs[p * NVP8 + j]);
                         prevs[p * NVP8 + j] = sum;
                         if (!multi) {
                             Wsm[(j / AW) * WS + j % AW] += (R)fx_to_float(dq);
-                        } else {  // CTA 0 forwards this GPU's total to every GPU's world table
-                            for (int r = 0; r < pe.world; ++r)
-                                red_add_u64_sys(reinterpret_cast<unsigned long long*>(pe.inbox[r]) + ((size_t)p * NV + j) * kAccStride,
+                        } else {  // group leader: the group total goes to every GPU's world table
+                            for (int r = 0; r < pe.world; ++r) {
+                                const int rr = (pe.rank + r) % pe.world;  // own table first, then the peers in a rank-rotated order
+                                red_add_u64_sys(reinterpret_cast<unsigned long long*>(pe.inbox[rr]) + ((size_t)p * NV + j) * AST,
                                                 ((unsigned long long)dq << 8) + 1ull);
+                            }
                         }
                     }
                 }
                 if (multi) {
-                    const unsigned long long cnt = (unsigned long long)pe.world * k;
-                    const unsigned long long* wtab = reinterpret_cast<const unsigned long long*>(pe.inbox[pe.rank]) + (size_t)p * NV * kAccStride;
+                    if (sy.poll_delay_ns > 0) __nanosleep((unsigned)sy.poll_delay_ns);
+                    const unsigned long long cnt = (unsigned long long)pe.world * (unsigned long long)NG * k;
+                    const unsigned long long* wtab = reinterpret_cast<const unsigned long long*>(pe.inbox[pe.rank]) + (size_t)p * NV * AST;
                     for (int j = tid; j < NV; j += BLOCK) {
-                        const unsigned long long* word = wtab + (size_t)j * kAccStride;
+                        const unsigned long long* word = wtab + (size_t)j * AST;
                         unsigned long long w = ld_u64_sys(word);
                         while ((w & 0xFFull) != (cnt & 0xFFull)) w = ld_u64_sys(word);
                         const long long sum = fx_running_sum(w, cnt);
@@ -758,9 +820,12 @@ __global__ void __launch_bounds__(512, 1) persistent_kernel(const StepArgs a, co
     }
     if (SHAREDW && b == 0) {
         for (int j = tid; j < FA; j += BLOCK) static_cast<R*>(a.W)[j] = Wsm[(j / AW) * WS + j % AW];
-        if (FX) {  // every CTA holds the same running sums (multi-GPU: only CTA 0 tracks the local table)
-            for (int j = tid; j < 4 * NV; j += BLOCK) sy.prev[j] = prevs[(j / NV) * NVP8 + j % NV];
+        if (FX) {  // every CTA holds the same running sums of the world table (one GPU: of the only table, saved below)
+            for (int j = tid; j < 2 * NV; j += BLOCK) sy.prev[j] = prevs[(2 + j / NV) * NVP8 + j % NV];
         }
+    }
+    if (SHAREDW && FX && b < (pe.world > 1 ? (sy.ngroups < G ? sy.ngroups : G) : 1)) {  // group leaders: their group's table
+        for (int j = tid; j < 2 * NV; j += BLOCK) sy.prev[(size_t)(2 + 2 * b) * NV + j] = prevs[(j / NV) * NVP8 + j % NV];
     }
     if (SHAREDW && CS > 1) cl_sync();  // nobody leaves while a bulk copy may still read or write its shared memory
 }

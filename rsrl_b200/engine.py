@@ -152,7 +152,7 @@ class Engine:
         """rsrl_engine_get_launch_shape as a dict (the fp32 summation order is a function of it: oracle/oracle32.cpp)."""
         out = np.zeros(24, dtype=np.int32)
         check(self.lib.rsrl_engine_get_launch_shape(self.h, ip(out)))
-        keys = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "lpg", "seg_len", "pe_smem", "world",
+        keys = ["persistent", "mode", "grid", "cluster_size", "n_clusters", "block", "lpr", "unused7", "unused8", "pe_smem", "world",
                 "rank", "peers", "smem", "tile", "f4", "fx"]
         return dict(zip(keys, (int(v) for v in out)))
 
