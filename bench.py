@@ -119,7 +119,10 @@ def attach_exchange(eng, dist, rank, world, want_peers):
         flag = torch.tensor([ok], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 1:
-            return "in-kernel exchange: cluster DSMEM + NVLink peer-memory LL words + L2 LL lines (fixed order)"
+            if eng.launch_shape()["fx"]:
+                return ("in-kernel exchange (fp32): 2^-40 fixed-point counting accumulators in L2, CTA-group tables whose leaders add the group "
+                        "totals to every GPU's world table with system-scope reductions over NVLink peer pointers (order independent)")
+            return "in-kernel exchange (f64): cluster DSMEM + NVLink peer-memory LL words + L2 LL lines (fixed order)"
         raise SystemExit("peer attach failed on some rank")
     uid = [comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)

@@ -129,6 +129,12 @@ static cudaError_t dispatch_fused(const BasisKey& k, int mode, bool ext, const S
                                                 {launch_fused_f64_d0, launch_fused_f64_d1, launch_fused_f64_d2}};
     return table[k.dtype][k.domain](k, mode, ext, a, grid, block, smem, st);
 }
+// the (basis, order) pair exists as template instantiations; otherwise the run-time-order kernels of dyn.cuh take the engine
+static bool has_static(const BasisKey& k) {
+    typedef bool (*fn)(const BasisKey&);
+    static const fn table[2][3] = {{has_static_f32_d0, has_static_f32_d1, has_static_f32_d2}, {has_static_f64_d0, has_static_f64_d1, has_static_f64_d2}};
+    return table[k.dtype][k.domain](k);
+}
 static cudaError_t dispatch_eval(const BasisKey& k, const EvalArgs& e, cudaStream_t st) {
     static const eval_launch_fn table[2][3] = {{launch_eval_f32_d0, launch_eval_f32_d1, launch_eval_f32_d2},
                                                {launch_eval_f64_d0, launch_eval_f64_d1, launch_eval_f64_d2}};
@@ -221,6 +227,7 @@ struct rsrl_engine {
     size_t stage_bytes = 0;
     uint32_t xepoch = 0;  // exchange epoch: counts batched steps over the engine's life, NOT reset by rsrl_engine_reset
     int pcap = 0;  // slot stride of the CTA reduce buffers
+    bool dyn = false;  // (basis, order) without template instantiation: run-time-order kernels (dyn.cuh)
     uint64_t t = 0;
     int64_t launches = 0;
     double epsilon = 0.0;
@@ -258,7 +265,9 @@ static int ensure_stage(rsrl_engine* e, size_t elems) {
 }
 
 static void choose_launch(rsrl_engine* e) {
-    if (e->cfg.weight_mode == RSRL_PER_ENV) {
+    if (e->dyn) {  // dyn.cuh: one warp per CTA, no shared memory
+        e->block = 32; e->smem = 0;
+    } else if (e->cfg.weight_mode == RSRL_PER_ENV) {
         e->block = 128; e->smem = 0;
     } else if (e->WT == 2) {  // twotable.cuh: W[2][FA] + phi(s) and phi(s') rows + three coefficient planes
         int block = 256;
@@ -301,7 +310,7 @@ static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
     const size_t ndc = e->has_trace ? 1 : (size_t)e->AW;
     const size_t nvp = (size_t)persist_nvp((int)e->FA, (int)e->rsz);
     const size_t ncl = (size_t)(grid / cs);
-    const size_t elems = (size_t)(2 + cs + (!e->sync.fx && ncl > 1 ? ncl : 0)) * nvp + (size_t)e->F * 4 + (size_t)(rows + ndc) * cap + (size_t)kPersistMaxWarps * nvp;
+    const size_t elems = (size_t)(2 + cs + (!e->sync.fx && ncl > 1 ? ncl : 0)) * nvp + (size_t)e->F * 4 + (size_t)(rows + ndc) * cap + (size_t)(block / 32) * nvp;
     size_t bytes = 16 + elems * e->rsz;
     if (e->sync.fx) bytes += (size_t)4 * ((e->FA + 1) / 2 * 2) * sizeof(long long);  // running sums of the counting exchange
     if (bytes > 220 * 1024) return false;
@@ -319,6 +328,7 @@ static bool persistent_shape(rsrl_engine* e, int grid, int cs) {
 static void choose_persistent(rsrl_engine* e) {
     e->persistent = false;
     e->pmode = e->cfg.weight_mode;
+    if (e->dyn) return;                                               // any-order coverage path: per-step kernels
     if (e->has_trace && e->cfg.weight_mode == RSRL_PER_ENV) return;  // per-env W + traces: per-step kernels
     if (e->WT == 2) return;                                           // GreedyGQ / A2C: per-step kernels (twotable.cuh)
     int dev = e->cfg.device, sms = 0;
@@ -554,7 +564,8 @@ int rsrl_engine_create(const rsrl_config_t* cfg, rsrl_engine_t** out) {
     e->has_trace = algo_has_trace(cfg->algo);
     e->WT = algo_two_tables(cfg->algo) ? 2 : 1;
     e->rsz = cfg->dtype == RSRL_F32 ? 4 : 8;
-    if (e->WT == 2 && (e->tile || e->f4)) {
+    e->dyn = !e->tile && !e->f4 && !has_static(e->key);
+    if (e->WT == 2 && (e->tile || e->f4 || e->dyn)) {
         delete e;
         return fail(RSRL_EUNSUPPORTED, "GreedyGQ / A2C are built for the Fourier / Polynomial bases of the register path");
     }

@@ -201,6 +201,8 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
     __host__ __device__ static constexpr double hi(int d) { return d == 0 ? 0.6 : 0.07; }
     __host__ __device__ static constexpr double start(int d) { return d == 0 ? -0.5 : 0.0; }
     __host__ __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
+    __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? 0.0 : -1.0; }  // :88-92
+    static constexpr bool kCheapStep = true;  // a transition costs ~100 instructions: all A candidates can be stepped ahead of time (persistent.cuh)
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double a = (double)(action - 1);                                        // ALL_ACTIONS = [-1, 0, 1]
@@ -265,6 +267,8 @@ template <> struct Domain<RSRL_CART_POLE> {
     __host__ __device__ __forceinline__ static bool is_terminal(const double* s) {  // :83-97
         return s[0] <= -2.4 || s[0] >= 2.4 || s[2] <= -TWELVE_DEGREES || s[2] >= TWELVE_DEGREES;
     }
+    __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? -1.0 : 0.0; }  // :23-24,103-107
+    static constexpr bool kCheapStep = false;
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double force = action == 0 ? -10.0 : 10.0;  // ALL_ACTIONS :26
@@ -301,6 +305,8 @@ template <> struct Domain<RSRL_ACROBOT> {
     __host__ __device__ __forceinline__ static bool is_terminal(const double* s) {  // :56-58
         return dadd(cos64(s[0]), cos64(dadd(s[0], s[1]))) < -1.0;
     }
+    __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? 0.0 : -1.0; }  // :32-33,134-138
+    static constexpr bool kCheapStep = false;
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double torque = (double)(action - 1);  // ALL_ACTIONS = [-1, 0, 1] :36
@@ -369,8 +375,10 @@ struct GridTables {
     R s[D][P];  // s[d][j] = sin(pi*(j+1)*x^_d)   (Polynomial: unused)
 };
 
+// grid_prepare = grid_prepare_base (per dimension: cos / sin of pi x^_d, or the raw x_d) + grid_expand (angle addition / powers).
+// The split lets the persistent kernel compute the base of a state ahead of time and expand it when the tables are needed.
 template <typename R, class Dom, int P, int BASIS>
-__host__ __device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom::D, P, BASIS>& t) {
+__host__ __device__ __forceinline__ void grid_prepare_base(const double* st, R (*base)[2]) {
     using O = RealOps<R>;
 #pragma unroll
     for (int d = 0; d < Dom::D; ++d) {
@@ -383,6 +391,21 @@ __host__ __device__ __forceinline__ void grid_prepare(const double* st, GridTabl
                                         : (R)ddiv(num, dsub(Dom::hi(d), Dom::lo(d)));
             R s1, c1;
             O::sincospi(xh, &s1, &c1);
+            base[d][0] = c1;
+            base[d][1] = s1;
+        } else {
+            base[d][0] = (R)st[d];
+            base[d][1] = (R)0;
+        }
+    }
+}
+template <typename R, class Dom, int P, int BASIS>
+__host__ __device__ __forceinline__ void grid_expand(const R (*base)[2], GridTables<R, Dom::D, P, BASIS>& t) {
+    using O = RealOps<R>;
+#pragma unroll
+    for (int d = 0; d < Dom::D; ++d) {
+        if (BASIS == RSRL_FOURIER) {
+            const R c1 = base[d][0], s1 = base[d][1];
             t.c[d][0] = c1;
             t.s[d][0] = s1;
 #pragma unroll
@@ -391,12 +414,18 @@ __host__ __device__ __forceinline__ void grid_prepare(const double* st, GridTabl
                 t.s[d][j] = O::fma(t.s[d][j - 1], c1, t.c[d][j - 1] * s1);
             }
         } else {
-            const R x = (R)st[d];
+            const R x = base[d][0];
             t.c[d][0] = x;
 #pragma unroll
             for (int j = 1; j < P; ++j) t.c[d][j] = t.c[d][j - 1] * x;
         }
     }
+}
+template <typename R, class Dom, int P, int BASIS>
+__host__ __device__ __forceinline__ void grid_prepare(const double* st, GridTables<R, Dom::D, P, BASIS>& t) {
+    R base[Dom::D][2];
+    grid_prepare_base<R, Dom, P, BASIS>(st, base);
+    grid_expand<R, Dom, P, BASIS>(base, t);
 }
 
 // complex helper on (re, im) pairs with compile-time "c == 0 => 1 + 0i" shortcut
@@ -407,11 +436,13 @@ struct GridBasis {
     using Tab = GridTables<R, D, P, BASIS>;
 
     // calls f(k, phi_k) for k = 0..F-1 in feature order; fully unrolled => k is a compile-time constant
-    template <class Fn>
+    // PAIR (device, fp32, D = 2, Fourier): two features per issue slot.  Measured: -2 % step time in the SHARED-weights kernel (14 warps per
+    // SM, latency bound), +50 % in the PER_ENV kernel (FMUL2 / FFMA2 issue at a fraction of the scalar rate) — so only the former asks for it.
+    template <bool PAIR = false, class Fn>
     __host__ __device__ __forceinline__ static void for_each(const Tab& t, Fn f) {
         using O = RealOps<R>;
 #ifdef __CUDA_ARCH__
-        if constexpr (D == 2 && BASIS == RSRL_FOURIER && sizeof(R) == 4) {
+        if constexpr (PAIR && D == 2 && BASIS == RSRL_FOURIER && sizeof(R) == 4) {
             // fp32 on the device: two features per issue slot (FMUL2 + FFMA2 with the dimension-0 entry broadcast from a scalar
             // register).  Per feature the operations are those of the scalar form below — (-s0) * s1 == -(s0 * s1) exactly —
             // so the host build (oracle32) keeps the scalar form.

@@ -139,6 +139,37 @@ static cudaError_t eval_one(const EvalArgs& e, cudaStream_t st) {
 #define RSRL_CAT_(a, b) a##b
 #define RSRL_CAT(a, b) RSRL_CAT_(a, b)
 
+bool RSRL_CAT(has_static_, RSRL_SUFFIX)(const BasisKey& k) {
+#define X(B, P) if (k.basis == B && k.order == P) return true;
+    RSRL_COMBOS(X)
+#undef X
+    return false;
+}
+
+#if !defined(RSRL_EMPTY)
+// run-time-order kernels (dyn.cuh): one warp per CTA
+template <int AW>
+static cudaError_t dyn_launch(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid, cudaStream_t st) {
+    const DynBasis b = {k.basis, k.order};
+    if (mode == RSRL_SHARED) {
+        if (ext) dyn_step_kernel<R, DOM, AW, RSRL_SHARED, true><<<grid, 32, 0, st>>>(a, b);
+        else dyn_step_kernel<R, DOM, AW, RSRL_SHARED, false><<<grid, 32, 0, st>>>(a, b);
+    } else {
+        if (ext) dyn_step_kernel<R, DOM, AW, RSRL_PER_ENV, true><<<grid, 32, 0, st>>>(a, b);
+        else dyn_step_kernel<R, DOM, AW, RSRL_PER_ENV, false><<<grid, 32, 0, st>>>(a, b);
+    }
+    return cudaGetLastError();
+}
+template <int AW>
+static cudaError_t dyn_eval(const BasisKey& k, const EvalArgs& e, cudaStream_t st) {
+    const DynBasis b = {k.basis, k.order};
+    const int block = 128, grid = (int)((e.n + block - 1) / block);
+    dyn_eval_kernel<R, DOM, AW><<<grid, block, 0, st>>>(e.mode, e.n, e.states, static_cast<const R*>(e.W), e.w_env_stride, e.out, e.act_out,
+                                                        e.pol, e.draw, e.env_offset, e.counters, b);
+    return cudaGetLastError();
+}
+#endif
+
 cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bool ext, const StepArgs& a, int grid,
                                                  int block, size_t smem, cudaStream_t st) {
     constexpr int A = Domain<DOM>::A;
@@ -149,6 +180,12 @@ cudaError_t RSRL_CAT(launch_fused_, RSRL_SUFFIX)(const BasisKey& k, int mode, bo
     }
     RSRL_COMBOS(X)
 #undef X
+#if !defined(RSRL_EMPTY)
+    if (k.basis != RSRL_TILE_CODING && k.order >= 1 && k.order <= kDynMaxOrder && block == 32 && smem == 0) {
+        if (k.aw == A) return dyn_launch<A>(k, mode, ext, a, grid, st);
+        if (k.aw == 1) return dyn_launch<1>(k, mode, ext, a, grid, st);
+    }
+#endif
     return cudaErrorInvalidDeviceFunction;
 }
 
@@ -203,6 +240,12 @@ cudaError_t RSRL_CAT(launch_eval_, RSRL_SUFFIX)(const BasisKey& k, const EvalArg
     }
     RSRL_COMBOS(X)
 #undef X
+#if !defined(RSRL_EMPTY)
+    if (k.basis != RSRL_TILE_CODING && k.order >= 1 && k.order <= kDynMaxOrder) {
+        if (k.aw == A) return dyn_eval<A>(k, e, st);
+        if (k.aw == 1) return dyn_eval<1>(k, e, st);
+    }
+#endif
     return cudaErrorInvalidDeviceFunction;
 }
 

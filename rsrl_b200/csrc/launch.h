@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "persistent.cuh"
 #include "twotable.cuh"
+#include "dyn.cuh"
 
 namespace rsrl {
 
@@ -41,7 +42,10 @@ typedef cudaError_t (*persist_launch_fn)(const BasisKey&, int weight_mode, const
 typedef cudaError_t (*two_launch_fn)(const BasisKey&, int weight_mode, bool ext, const StepArgs&, int grid, int block, size_t smem, cudaStream_t);
 typedef cudaError_t (*rollout_launch_fn)(const BasisKey&, const RolloutArgs&, cudaStream_t);
 
+// has_static_*: the (basis, order) pair is instantiated as templates in this unit; otherwise launch_fused_* / launch_eval_* run the
+// run-time-order kernels of dyn.cuh (launch_fused_* then wants block == 32 and no shared memory)
 #define RSRL_DECL_INST(SUFFIX)                                                                                      \
+    bool has_static_##SUFFIX(const BasisKey&);                                                                      \
     cudaError_t launch_two_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t);   \
     cudaError_t launch_rollout_##SUFFIX(const BasisKey&, const RolloutArgs&, cudaStream_t);                         \
     cudaError_t launch_fused_##SUFFIX(const BasisKey&, int, bool, const StepArgs&, int, int, size_t, cudaStream_t); \

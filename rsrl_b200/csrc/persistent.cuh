@@ -245,6 +245,18 @@ __device__ __forceinline__ void row_butterfly(R* v, int lpr) {
 template <typename R> struct Vec16;  // 16-byte shared-memory vector of R
 template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
+// Makes the compiler forget what it knows about the table values (no instructions): features generated from them afterwards are
+// recomputed instead of being kept in registers (and spilled) since their last use.
+__device__ __forceinline__ void launder(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void launder(double& x) { asm volatile("" : "+d"(x)); }
+template <typename R, int D, int P, int BASIS>
+__device__ __forceinline__ void launder_tab(GridTables<R, D, P, BASIS>& t) {
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int j = 0; j < P; ++j) { launder(t.c[d][j]); launder(t.s[d][j]); }
+}
+
 // acc[0] += p.even * d.even, acc[1] += p.odd * d.odd over the slots of one 16-byte group, in slot order
 __device__ __forceinline__ void pair_fma(const float4& p, const float4& d, float* acc) {
     float2 a = make_float2(acc[0], acc[1]);
@@ -277,14 +289,14 @@ __host__ __device__ constexpr int persist_cap(int block, int rsz) { return block
 // A compile-time stride whenever the rows fit (every STS / LDS of the env phase gets an immediate offset instead of an address
 // computation: -70 instructions per env-step on Fourier(5)); otherwise persist_cap(blockDim) at run time.
 __host__ __device__ constexpr int persist_cap_static(int rows, int rsz, bool trace) {
-    return (!trace && (long long)rows * persist_cap(kPersistMaxBlock, rsz) * rsz <= 160 * 1024) ? persist_cap(kPersistMaxBlock, rsz) : 0;
+    return (!trace && (long long)rows * persist_cap(kPersistMaxBlock, rsz) * rsz <= 96 * 1024) ? persist_cap(kPersistMaxBlock, rsz) : 0;
 }
 
 // NV values of R padded to a multiple of 16 bytes (bulk copies); host and device lay the shared memory out from this
 __host__ __device__ constexpr int persist_nvp(int nv, int rsz) { return (nv * rsz + 15) / 16 * 16 / rsz; }
 
 template <typename R, int DOM, int BASIS, int P, int AW, int MODE>
-__global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock, MODE == RSRL_PER_ENV ? 4 : 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
+__global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const StepArgs a, const int k_steps, const SyncArgs sy, const PeerArgs pe) {
     using Dom = Domain<DOM>;
     using GB = GridBasis<R, Dom::D, P, BASIS>;
     using O = RealOps<R>;
@@ -332,15 +344,15 @@ __global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock,
     R* Wsm = inbuf + (size_t)CS * NVP;        // [FApad]
     R* red = Wsm + FApad;                     // [ROWS][cap]  phi(s_t) feature-major, or the traces z[F*A][slot]
     R* dcs = red + (size_t)ROWS * cap;        // [NDC][cap]   scaled TD error in the action's row, 0 elsewhere
-    R* wpart = dcs + (size_t)NDC * cap;       // [kPersistMaxWarps][NVP] warp partials of the CTA reduce
-    R* gath = wpart + (size_t)kPersistMaxWarps * NVP;  // [n_clusters][NVP] leader: the clusters' partials gathered from L2 (only when n_clusters > 1)
+    R* wpart = dcs + (size_t)NDC * cap;       // [BLOCK / 32][NVP] warp partials of the CTA reduce
+    R* gath = wpart + (size_t)(BLOCK >> 5) * NVP;  // [n_clusters][NVP] leader: the clusters' partials gathered from L2 (only when n_clusters > 1)
     // counting exchange: running sums seen at the previous completion [4][NVP8] (local parity 0, 1; world parity 0, 1); it takes gath's place
     long long* prevs = reinterpret_cast<long long*>(gath);
     const uint32_t mb_in = cl_smem_u32(&mbars[0]), mb_tot = cl_smem_u32(&mbars[1]);
 
     if (SHAREDW) {
         for (int j = tid; j < FA; j += BLOCK) Wsm[(j / AW) * WS + j % AW] = static_cast<const R*>(a.W)[j];
-        for (int j = tid; j < (ROWS + NDC) * cap + kPersistMaxWarps * NVP; j += BLOCK) red[j] = (R)0;
+        for (int j = tid; j < (ROWS + NDC) * cap + (BLOCK >> 5) * NVP; j += BLOCK) red[j] = (R)0;
         for (int j = tid; j < NVP; j += BLOCK) { part[j] = (R)0; totbuf[j] = (R)0; }
         if (FX) {
             // running sums at the previous completion: rows 0, 1 = the table this CTA polls (one GPU: the only table; several GPUs:
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock,
                         asm volatile("" ::: "memory");
                         float2 q01 = make_float2(0.0f, 0.0f), q23 = make_float2(0.0f, 0.0f);
                         float q2 = 0.0f;
-                        GB::for_each(tab, [&](int k, R phi) {
+                        GB::template for_each<true>(tab, [&](int k, R phi) {
                             if (decltype(rec)::value) red[k * cap + tid] = phi;
                             const float4 w = *reinterpret_cast<const float4*>(Wsm + k * WS);
                             q01 = ffma2(make_float2(phi, phi), make_float2(w.x, w.y), q01);
@@ -479,6 +491,7 @@ __global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock,
                 if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
                 if (MODE == RSRL_PER_ENV) {
                     R* Wm = static_cast<R*>(a.W);
+                    launder_tab(tab_s);  // regenerate phi(s_t) from the tables: keeping the F values of evalS alive until here spills them
                     GB::for_each(tab_s, [&](int k, R phi) {
                         const int col = k * AW + (TDPRED ? 0 : o.act);
                         if (pe_smem) {
@@ -579,9 +592,9 @@ __global__ void __launch_bounds__(MODE == RSRL_PER_ENV ? 128 : kPersistMaxBlock,
             // CTA partial: the warp partials added in warp order (thread j owns value j)
             const int NW = BLOCK >> 5;
             for (int j = tid; j < NV; j += BLOCK) {
-                R v[kPersistMaxWarps];  // all loads first (rows of warps >= NW hold zeros): one shared-memory latency, not NW
+                R v[kPersistMaxWarps];  // all loads first: one shared-memory latency, not NW
 #pragma unroll
-                for (int w = 0; w < kPersistMaxWarps; ++w) v[w] = wpart[(size_t)w * NVP + j];
+                for (int w = 0; w < kPersistMaxWarps; ++w) v[w] = w < NW ? wpart[(size_t)w * NVP + j] : (R)0;
                 R acc = v[0];
 #pragma unroll
                 for (int w = 1; w < kPersistMaxWarps; ++w) if (w < NW) acc += v[w];

@@ -456,9 +456,102 @@ def test_learning_happens(E):
 
 
 def test_unsupported_combination_fails_loudly(E):
+    # two-table agents exist for the instantiated MountainCar bases only; an order without templates has no two-table kernel
     with pytest.raises(abi.RsrlError) as ei:
-        E.Engine(abi.default_config(basis_order=4))
+        E.Engine(abi.default_config(basis_order=4, algo=abi.GREEDY_GQ))
     assert ei.value.code == abi.EUNSUPPORTED
+    with pytest.raises(abi.RsrlError) as ei:
+        E.Engine(abi.default_config(basis_order=8))
+    assert ei.value.code == abi.EINVAL
+
+
+# ---------------------------------------------------------------------------------------------
+# ANY basis order (lfa takes any; csrc/dyn.cuh runs the (basis, order) pairs that have no template instantiation)
+# ---------------------------------------------------------------------------------------------
+DYN_COMBOS = [(MC, abi.FOURIER, 4), (MC, abi.FOURIER, 6), (MC, abi.POLYNOMIAL, 1), (MC, abi.POLYNOMIAL, 5),
+              (CP, abi.FOURIER, 1), (CP, abi.FOURIER, 4), (AC, abi.POLYNOMIAL, 3), (AC, abi.FOURIER, 6)]
+
+
+@pytest.mark.parametrize("domain,basis,order", DYN_COMBOS)
+@pytest.mark.parametrize("dtype,tol", [(abi.F64, 1e-12), (abi.F32, 2e-4)])
+def test_any_order_project_and_evaluate_match_oracle(E, oracle, domain, basis, order, dtype, tol):
+    cfg = abi.default_config(domain=domain, basis=basis, basis_order=order, dtype=dtype)
+    D, A = oracle.domain_dims(domain)
+    F = oracle.n_features(cfg)
+    assert F == (order + 1) ** D
+    lo, hi = oracle.domain_limits(domain)
+    rng = np.random.default_rng(order)
+    s = rng.uniform(lo, hi, size=(200, D))
+    s[0], s[1] = lo, hi
+    got, want = E.basis_project(cfg, s), oracle.project(cfg, s)
+    assert got.shape == want.shape == (200, F)
+    scale = np.maximum(np.abs(want), 1.0)
+    assert (np.abs(got - want) / scale).max() < tol * (order if basis == abi.FOURIER else 1)
+    W = rng.normal(size=(F, A))
+    q_got, q_want = E.lfa_evaluate(cfg, W, s), oracle.evaluate(cfg, W, s)   # (Polynomial features of raw Acrobot states reach 1e10: relative)
+    assert (np.abs(q_got - q_want) / np.maximum(np.abs(q_want), 1.0)).max() < tol * np.sqrt(F) * (order if basis == abi.FOURIER else 1)
+
+
+def test_any_order_features_equal_the_template_path(E):
+    """The run-time-order kernels generate the same bits as the templates: phi[c0, c1] = cos(pi (c0 x0 + c1 x1)) does not
+    depend on the order P, so the order-4 grid (dyn.cuh) is a sub-grid of the order-5 grid (templates), which is a sub-grid
+    of the order-6 grid (dyn.cuh)."""
+    rng = np.random.default_rng(3)
+    s = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(64, 2))
+    f5 = E.basis_project(abi.default_config(basis_order=5, dtype=abi.F32), s).reshape(64, 6, 6)   # templates; index [5 - c0, 5 - c1]
+    f4 = E.basis_project(abi.default_config(basis_order=4, dtype=abi.F32), s).reshape(64, 5, 5)   # dyn.cuh;   index [4 - c0, 4 - c1]
+    f6 = E.basis_project(abi.default_config(basis_order=6, dtype=abi.F32), s).reshape(64, 7, 7)
+    assert (f4 == f5[:, 1:, 1:]).all()        # same coefficient vectors, same arithmetic: same bits
+    assert (f6[:, 1:, 1:] == f5).all()
+
+
+@pytest.mark.parametrize("domain,basis,order,algo,mode", [
+    (MC, abi.FOURIER, 4, abi.QLEARNING, abi.SHARED), (MC, abi.FOURIER, 6, abi.SARSA, abi.PER_ENV),
+    (MC, abi.POLYNOMIAL, 5, abi.EXPECTED_SARSA, abi.SHARED), (MC, abi.FOURIER, 4, abi.SARSA_LAMBDA, abi.SHARED),
+    (MC, abi.FOURIER, 4, abi.Q_LAMBDA, abi.PER_ENV), (MC, abi.FOURIER, 6, abi.TD_LAMBDA, abi.SHARED),
+    (CP, abi.FOURIER, 1, abi.SARSA, abi.SHARED), (AC, abi.FOURIER, 4, abi.EXPECTED_SARSA, abi.SHARED)])
+def test_any_order_engine_free_run_f64(E, oracle, domain, basis, order, algo, mode):
+    D = 2 if domain == MC else 4
+    lo0 = [-0.6, 0.0] if domain == MC else [-0.05] * 4
+    hi0 = [-0.4, 0.0] if domain == MC else [0.05] * 4
+    pred = algo == abi.TD_LAMBDA
+    cfg = abi.default_config(domain=domain, basis=basis, basis_order=order, algo=algo, weight_mode=mode,
+                             policy=abi.RANDOM if pred else abi.EPSILON_GREEDY, epsilon=0.1, n_envs=77, dtype=abi.F64,
+                             init_mode=abi.INIT_UNIFORM, init_lo=lo0, init_hi=hi0, max_episode_steps=40, seed=11, gamma=0.99,
+                             lr=0.01, alpha=0.01 if algo in (abi.SARSA_LAMBDA, abi.Q_LAMBDA) else 0.5, lambda_=0.5,
+                             update_scale=abi.SCALE_MEAN, record_td_error=1)
+    steps = 12 if pred else 90
+    with E.Engine(cfg) as e:
+        assert e.launch_shape()["persistent"] == 0
+        o = oracle.Engine(cfg)
+        for chunk in (1, steps):
+            e.step(chunk)
+            o.step(chunk)
+            e.sync()
+            _compare_engines(e, o, w_tol=1e-9)
+        if algo in (abi.SARSA_LAMBDA, abi.Q_LAMBDA, abi.TD_LAMBDA):
+            assert np.abs(e.traces() - o.traces()).max() < 1e-9 * max(1.0, np.abs(o.traces()).max())
+        assert pred or o.stats()["total_episodes"] > 0
+
+
+def test_any_order_handle_entry_point(E, oracle):
+    """Handler::handle on explicit transitions (EXT kernels) for an order without templates."""
+    cfg = abi.default_config(basis_order=4, dtype=abi.F64, n_envs=50, lr=0.05, update_scale=abi.SCALE_MEAN)
+    rng = np.random.default_rng(5)
+    s0 = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(50, 2))
+    s1 = rng.uniform([-1.2, -0.07], [0.6, 0.07], size=(50, 2))
+    a = rng.integers(0, 3, 50).astype(np.int32)
+    r = -np.ones(50)
+    term = np.zeros(50, dtype=np.uint8)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        W0 = rng.normal(size=(25, 3)) * 0.1
+        e.set_weights(W0)
+        o.set_weights(W0)
+        e.handle(s0, a, r, s1, term)
+        o.handle(s0, a, r, s1, term)
+        e.sync()
+        assert np.abs(e.weights() - o.weights()).max() < 1e-12
 
 
 # ---------------------------------------------------------------------------------------------
