@@ -221,8 +221,9 @@ int rsrl_comm_unique_id(uint8_t out[128]);                      /* ncclGetUnique
 int rsrl_engine_comm_init(rsrl_engine_t* e, const uint8_t id[128], int rank, int world);
 /* In-kernel exchange over NVLink peer memory (preferred; world <= 8 GPUs of one box): every rank exports the
  * cudaIpc handle of its dW mailbox, the host gathers the handles (any transport) and attaches them; from then
- * on rsrl_engine_step keeps the persistent kernel and sums dW across GPUs inside it, in rank order.
- * All ranks must call reset / step with the same arguments and in lockstep. */
+ * on rsrl_engine_step keeps the persistent kernel and sums dW across GPUs inside it (fp32: order-independent fixed-point
+ * sums; f64: in rank order).  Attach before the engine's first step (RSRL_EINVAL afterwards: the exchange tables count
+ * arrivals from step 0).  All ranks must call reset / step with the same arguments and in lockstep. */
 int rsrl_engine_peer_export(rsrl_engine_t* e, uint8_t handle_out[64]);
 int rsrl_engine_peer_attach(rsrl_engine_t* e, const uint8_t* handles /* world x 64 */, int rank, int world);
 

@@ -13,7 +13,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--expt-relaxed-constexpr"]
 # --fmad=false for the units whose arithmetic oracle/oracle32.cpp reproduces bit for bit: every FMA there is explicit (hostdev.h)
 NOFMAD = ["--fmad=false"]
-HEADERS = ["hostdev.h", "device.cuh", "core.cuh", "kernels.cuh", "persistent.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
+HEADERS = ["hostdev.h", "device.cuh", "core.cuh", "kernels.cuh", "persistent.cuh", "dyn.cuh", "tile.cuh", "fourier4.cuh", "launch.h", os.path.join("..", "..", "include", "rsrl_b200.h")]
 
 
 # headers only some translation units include (kept out of HEADERS so that editing them does not rebuild everything)
@@ -52,7 +52,13 @@ def build(force=False, verbose=False):
     # The library is newer than every source: nothing to do, even when the object files did not travel with the tree
     # (the GPU box receives the prebuilt .so without csrc/build/).
     srcs = sorted({os.path.join(CSRC, u[1]) for u in _units()}) + [os.path.join(CSRC, h) for hs in EXTRA_DEPS.values() for h in hs]
-    if not force and not _stale(LIB, srcs + hdrs):
+    def _objects_fresh():  # (an RSRL_BUILD_ONLY build relinks the library over objects that are older than the headers)
+        for obj, src, _ in _units():
+            o = os.path.join(OBJ, obj)
+            if os.path.exists(o) and _stale(o, [os.path.join(CSRC, src)] + hdrs + [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(src, [])]):
+                return False
+        return True
+    if not force and not _stale(LIB, srcs + hdrs) and _objects_fresh():
         return LIB
     jobs = []
     # RSRL_BUILD_ONLY=inst_f32_d0,abi (development only): recompile just these objects, trust the others if they exist

@@ -100,7 +100,8 @@ static int64_t n_features(const rsrl_config_t* c) {
     return c->basis == RSRL_TILE_CODING ? c->memory_size : ipow(c->basis_order + 1, dom_dim(c->domain));
 }
 static TileParams tile_params(const rsrl_config_t* c) {
-    TileParams tp; tp.n_tilings = c->n_tilings; tp.tiles_per_dim = c->tiles_per_dim; tp.memory_mask = c->memory_size - 1; return tp;
+    TileParams tp; tp.n_tilings = c->n_tilings; tp.tiles_per_dim = c->tiles_per_dim; tp.memory_mask = c->memory_size - 1;
+    tp.div_magic = tile_div_magic(c->n_tilings); return tp;
 }
 
 static bool is_f4(const rsrl_config_t* c) {

@@ -41,34 +41,51 @@ __host__ __device__ __forceinline__ double dwrap(double lb, double x, double ub)
 // on [-pi/4, pi/4]); sincospi32 < 1 ulp (reduction x - rint(2x)/2 is exact); exp32 < 1 ulp.
 // Outside those ranges (never reached by the bounded domains) the platform libm is used.
 // ---------------------------------------------------------------------------
+// The f64 constants of the reduction and of the two kernels.  On the device they come from constant memory: as literals the compiler
+// materialises each one with two UMOV per use (52 extra issue slots per MountainCar step, 190 per CartPole RK4 step); as a constant-bank
+// operand they are free.  Same values on both sides.
+#if defined(__CUDACC__)
+static __constant__ double kMath64[16] = {
+    0.63661977236758138, -1.5707963267948966, -6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+#endif
+#ifdef __CUDA_ARCH__
+#define RSRL_M64(i, literal) kMath64[i]
+#else
+#define RSRL_M64(i, literal) (literal)
+#endif
+
 // x = n*pi/2 + (r + lo), |r| <= pi/4 + eps, |lo| < ulp(r); returns n mod 4
 __host__ __device__ __forceinline__ int rem_pio2_64(double x, double& r, double& lo) {
-    const double n = rint(dmul(x, 0.63661977236758138));          // 2/pi
-    const double r1 = dfma(n, -1.5707963267948966, x);            // exact: x and n*P1 cancel to <= 53 bits
-    r = dfma(n, -6.123233995736766e-17, r1);
-    lo = dfma(n, -6.123233995736766e-17, dsub(r1, r));            // the rounding error of r ...
-    lo = dfma(n, -1.4973849048591698e-33, lo);                    // ... and the third part of pi/2
+    const double n = rint(dmul(x, RSRL_M64(0, 0.63661977236758138)));          // 2/pi
+    const double r1 = dfma(n, RSRL_M64(1, -1.5707963267948966), x);            // exact: x and n*P1 cancel to <= 53 bits
+    r = dfma(n, RSRL_M64(2, -6.123233995736766e-17), r1);
+    lo = dfma(n, RSRL_M64(2, -6.123233995736766e-17), dsub(r1, r));            // the rounding error of r ...
+    lo = dfma(n, RSRL_M64(3, -1.4973849048591698e-33), lo);                    // ... and the third part of pi/2
     return (int)n & 3;
 }
 __host__ __device__ __forceinline__ double sin_kernel64(double r, double lo) {  // sin(r + lo)
     const double z = dmul(r, r);
-    double p = 1.58969099521155010221e-10;
-    p = dfma(p, z, -2.50507602534068634195e-08);
-    p = dfma(p, z, 2.75573137070700676789e-06);
-    p = dfma(p, z, -1.98412698298579493134e-04);
-    p = dfma(p, z, 8.33333333332248946124e-03);
-    p = dfma(p, z, -1.66666666666666324348e-01);
+    double p = RSRL_M64(4, 1.58969099521155010221e-10);
+    p = dfma(p, z, RSRL_M64(5, -2.50507602534068634195e-08));
+    p = dfma(p, z, RSRL_M64(6, 2.75573137070700676789e-06));
+    p = dfma(p, z, RSRL_M64(7, -1.98412698298579493134e-04));
+    p = dfma(p, z, RSRL_M64(8, 8.33333333332248946124e-03));
+    p = dfma(p, z, RSRL_M64(9, -1.66666666666666324348e-01));
     const double corr = dfma(dmul(r, z), p, dmul(lo, dfma(z, -0.5, 1.0)));  // r^3 p(z) + lo cos(r)
     return dadd(r, corr);
 }
 __host__ __device__ __forceinline__ double cos_kernel64(double r, double lo) {  // cos(r + lo)
     const double z = dmul(r, r);
-    double p = -1.13596475577881948265e-11;
-    p = dfma(p, z, 2.08757232129817482790e-09);
-    p = dfma(p, z, -2.75573143513906633035e-07);
-    p = dfma(p, z, 2.48015872894767294178e-05);
-    p = dfma(p, z, -1.38888888888741095749e-03);
-    p = dfma(p, z, 4.16666666666666019037e-02);
+    double p = RSRL_M64(10, -1.13596475577881948265e-11);
+    p = dfma(p, z, RSRL_M64(11, 2.08757232129817482790e-09));
+    p = dfma(p, z, RSRL_M64(12, -2.75573143513906633035e-07));
+    p = dfma(p, z, RSRL_M64(13, 2.48015872894767294178e-05));
+    p = dfma(p, z, RSRL_M64(14, -1.38888888888741095749e-03));
+    p = dfma(p, z, RSRL_M64(15, 4.16666666666666019037e-02));
     const double h = dfma(z, -0.5, 1.0);                           // 1 - z/2 and its rounding error e
     const double e = dfma(z, -0.5, dsub(1.0, h));
     return dadd(h, dadd(e, dfma(dmul(z, z), p, -dmul(r, lo))));    // + z^2 p(z) - lo sin(r)
@@ -553,12 +570,26 @@ struct GridBasis {
 // ---------------------------------------------------------------------------
 constexpr int kMaxTilings = 16;
 struct TileTab {
-    int32_t idx[kMaxTilings];  // unique active rows, idx[0..n)
+    int32_t idx[kMaxTilings];  // idx[t], t < n: the row of tiling t, or -1 when an earlier tiling already activated that row (the set of active
+                               // rows is what counts: a HashMap of activations collapses duplicates); walk it in order and skip the -1s
     int n;
 };
 struct TileParams {
     int n_tilings, tiles_per_dim, memory_mask;
+    uint32_t div_magic;  // ceil(2^32 / n_tilings): n / n_tilings == umulhi(n, div_magic) for 0 <= n < 2^24 (host: tile_div_magic)
 };
+__host__ __device__ __forceinline__ uint32_t tile_div_magic(int n_tilings) {
+    return (uint32_t)((0x100000000ull + (uint64_t)n_tilings - 1ull) / (uint64_t)n_tilings);
+}
+// (q + offset) / n_tilings, 32 times per state: the run-time divisor costs ~20 instructions per division on the GPU (half of
+// the TileCoding kernel's instructions); multiply-high by the precomputed reciprocal is exact for the small non-negative
+// numerators of in-range states (n * (magic * T - 2^32) < 2^32 holds for n < 2^28, T <= 16); anything else divides.
+__host__ __device__ __forceinline__ int32_t tile_div(int32_t n, const TileParams& tp) {
+#ifdef __CUDA_ARCH__
+    if (n >= 0 && n < (1 << 24)) return (int32_t)__umulhi((uint32_t)n, tp.div_magic);
+#endif
+    return n / tp.n_tilings;
+}
 
 __host__ __device__ __forceinline__ uint32_t tile_hash(uint32_t tiling, const int32_t* coord, int D) {
     uint32_t h = (tiling + 1u) * 0x9E3779B1u;
@@ -576,22 +607,18 @@ __host__ __device__ __forceinline__ void tile_prepare(const double* st, const Ti
         const double xh = ddiv(dsub(st[d], Dom::lo(d)), dsub(Dom::hi(d), Dom::lo(d)));
         q[d] = (int32_t)floor(dmul(dmul(xh, (double)tp.tiles_per_dim), (double)tp.n_tilings));
     }
-    tab.n = 0;
+    tab.n = tp.n_tilings;
 #pragma unroll
     for (int t = 0; t < TMAX; ++t) {
         if (t < tp.n_tilings) {
             int32_t coord[Dom::D];
 #pragma unroll
-            for (int d = 0; d < Dom::D; ++d) coord[d] = (q[d] + t * (1 + 2 * d)) / tp.n_tilings;
+            for (int d = 0; d < Dom::D; ++d) coord[d] = tile_div(q[d] + t * (1 + 2 * d), tp);
             const int32_t row = (int32_t)(tile_hash((uint32_t)t, coord, Dom::D) & (uint32_t)tp.memory_mask);
             bool dup = false;
 #pragma unroll
-            for (int j = 0; j < TMAX; ++j) dup |= (j < tab.n) && tab.idx[j] == row;
-            if (!dup) {
-#pragma unroll
-                for (int j = 0; j < TMAX; ++j) if (j == tab.n) tab.idx[j] = row;  // register-friendly insert
-                tab.n += 1;
-            }
+            for (int j = 0; j < t; ++j) dup |= tab.idx[j] == row;  // (earlier duplicates are -1: they never match)
+            tab.idx[t] = dup ? -1 : row;
         }
     }
 }

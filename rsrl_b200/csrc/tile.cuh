@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs 
         for (int c = 0; c < AW; ++c) q[c] = (R)0;
 #pragma unroll
         for (int j = 0; j < kMaxTilings; ++j) {
-            if (j < tab.n) {
+            if (j < tab.n && tab.idx[j] >= 0) {
 #pragma unroll
                 for (int c = 0; c < AW; ++c) q[c] += Wsm[tab.idx[j] * AW + c];  // activation 1.0
             }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs 
                 const int col = TDPRED ? 0 : o.act;
 #pragma unroll
                 for (int j = 0; j < kMaxTilings; ++j)
-                    if (j < tab_s.n) atomicAdd(Gt + (size_t)tab_s.idx[j] * AW + col, (unsigned long long)fx);
+                    if (j < tab_s.n && tab_s.idx[j] >= 0) atomicAdd(Gt + (size_t)tab_s.idx[j] * AW + col, (unsigned long long)fx);
                 if (!EXT) {
                     a.ep_steps[i] = env_bookkeeping<Dom>(a, t, i, g, s, a.ep_steps[i], o.terminated);
                     a.actions[i] = o.act;
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(512, 1) tile_persistent_kernel(const StepArgs 
 // contributions into a shared-memory fixed-point table (integer adds: order independent => bit-reproducible), then the
 // tables are summed across CTAs with a dense reduce-scatter through L2:
 //   P[b][*] = CTA b's table  | grid barrier |  CTA b sums its slice of all P[*]  -> T  | grid barrier |  every CTA reads T.
-// ~28 MB of L2 traffic and two counter barriers per step instead of the atomics.
+// (round 1; ~28 MB of L2 traffic and two counter barriers per step instead of the atomics).  Round 2: the per-CTA tables are sparse, so
+// each CTA pushes only its non-zero entries into a rotating global table with integer reductions: one barrier, ~1/50 of the traffic.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier_local(unsigned long long* counter, unsigned long long target) {
     __syncthreads();
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
         for (int c = 0; c < AW; ++c) q[c] = (R)0;
 #pragma unroll
         for (int j = 0; j < TMAX; ++j) {
-            if (j < tab.n) {
+            if (j < tab.n && tab.idx[j] >= 0) {
 #pragma unroll
                 for (int c = 0; c < AW; ++c) q[c] += Wsm[tab.idx[j] * AW + c];  // activation 1.0
             }
@@ -170,9 +171,6 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
     };
     auto prep = [&](const double* st, TileTab& tb) { tile_prepare<Dom, TMAX>(st, ta.tp, tb); };
     const double inv_fx = 1.0 / ta.fx_scale;
-    unsigned long long* P = ta.G;                          // [G][MA]
-    unsigned long long* T = ta.G + (size_t)G * MA;         // [MA]
-    const int slice = (MA + G - 1) / G;                    // entries of T owned by one CTA
 
     for (int step = 0; step < k_steps; ++step) {
         const uint64_t t = a.t + (uint64_t)step;
@@ -205,11 +203,12 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
                 }
             }
             // dW[row, a_t] += coef for every active row (activation 1.0).  When the whole warp hits the same entry (envs
-            // start in the same tiles) the warp adds once.
+            // start in the same tiles) the warp adds once.  (Grouping the lanes by entry with match.any + three 32-bit warp
+            // reductions per tiling instead: 132 us per step against 40 — measured, profiles/r02_cfg3_tile.md.)
 #pragma unroll
             for (int j = 0; j < TMAX; ++j) {
                 if (j >= ta.tp.n_tilings) break;  // uniform
-                const int key = (active && j < tab_s.n) ? tab_s.idx[j] * AW + col : -1;
+                const int key = (active && j < tab_s.n && tab_s.idx[j] >= 0) ? tab_s.idx[j] * AW + col : -1;
                 int same;
                 __match_all_sync(0xffffffffu, key, &same);
                 if (same) {
@@ -226,21 +225,20 @@ __global__ void __launch_bounds__(MAXT, 1) tile_dense_kernel(const StepArgs a, c
         }
         __syncthreads();
         if (G > 1) {
-            // publish this CTA's table (and clear it for the next step)
-            unsigned long long* Pb = P + (size_t)b * MA;
-            for (int j = tid; j < MA; j += BLOCK) { __stcg(Pb + j, Gs[j]); Gs[j] = 0ull; }
-            grid_barrier_local(ta.barrier, (unsigned long long)(2 * step + 1) * (unsigned long long)G);
-            // reduce-scatter: this CTA sums entries [b*slice, (b+1)*slice) over all partials; warp per entry, lanes over CTAs
-            const int e0 = b * slice, e1 = e0 + slice < MA ? e0 + slice : MA;
-            for (int e = e0 + (tid >> 5); e < e1; e += BLOCK >> 5) {
-                long long v = 0;
-                for (int g2 = lane; g2 < G; g2 += 32) v += (long long)__ldcg(P + (size_t)g2 * MA + e);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) __stcg(T + e, (unsigned long long)v);
+            // sparse push: only the entries this CTA touched (a few hundred of M * A: the envs crowd into few tiles) are added to the
+            // step's global table with 64-bit integer reductions (order independent); ONE grid barrier; every CTA reads the table.
+            // Three tables rotate by step: accumulate + read t, (t + 1), and the one being cleared for t + 2 — it was read during step
+            // t - 1, and every CTA has left that phase before it arrives at this step's barrier.
+            const unsigned long long rot = ta.barrier_base + (unsigned long long)step;
+            unsigned long long* Tt = ta.G + (size_t)(rot % 3ull) * MA;
+            unsigned long long* Tz = ta.G + (size_t)((rot + 2ull) % 3ull) * MA;
+            for (int j = tid; j < MA; j += BLOCK) {
+                const unsigned long long v = Gs[j];
+                if (v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(Tt + j), "l"(v) : "memory"); Gs[j] = 0ull; }
             }
-            grid_barrier_local(ta.barrier, (unsigned long long)(2 * step + 2) * (unsigned long long)G);
-            for (int j = tid; j < MA; j += BLOCK) Wsm[j] += (R)((double)(long long)__ldcg(T + j) * inv_fx);
+            grid_barrier_local(ta.barrier, (unsigned long long)(step + 1) * (unsigned long long)G);
+            for (int j = tid; j < MA; j += BLOCK) Wsm[j] += (R)((double)(long long)__ldcg(Tt + j) * inv_fx);
+            for (int j = b * BLOCK + tid; j < MA; j += G * BLOCK) Tz[j] = 0ull;
         } else {
             for (int j = tid; j < MA; j += BLOCK) { Wsm[j] += (R)((double)(long long)Gs[j] * inv_fx); Gs[j] = 0ull; }
         }
@@ -265,13 +263,14 @@ __global__ void tile_eval_kernel(int mode, int64_t n, const double* __restrict__
     tile_prepare<Dom>(s, tp, tab);
     const int M = tp.memory_mask + 1;
     if (mode == 0) {
-        for (int j = 0; j < tab.n; ++j) out[i * M + tab.idx[j]] = 1.0;  // `out` is zero-filled by the host
+        for (int j = 0; j < tab.n; ++j) if (tab.idx[j] >= 0) out[i * M + tab.idx[j]] = 1.0;  // `out` is zero-filled by the host
         return;
     }
     R q[AW];
 #pragma unroll
     for (int c = 0; c < AW; ++c) q[c] = (R)0;
     for (int j = 0; j < tab.n; ++j) {
+        if (tab.idx[j] < 0) continue;
 #pragma unroll
         for (int c = 0; c < AW; ++c) q[c] += W[tab.idx[j] * AW + c];
     }
