@@ -308,7 +308,12 @@ def main():
     # ---- N > 1: the W replicas must be bit-identical and agree with one GPU running all the envs ----
     checks = {}
     if world > 1:
-        H = 40 if shape["persistent"] else 6
+        # Horizon: 2 batched steps for the persistent engines (step 1 checks the cross-GPU sum, step 2 that every replica applied it).
+        # Not longer: 1 and N GPUs round the per-CTA fp32 partials differently (1e-7), and this workload (greedy, zero initial
+        # weights, reward -1) sits on a knife edge — from step 3 on a 1e-7 difference in W flips the argmax of a large fraction of the
+        # envs at once; the CPU replay of the device arithmetic shows the same 9e-5 jump at step 3 and 3.7e-4 after 40 steps for
+        # 8 x 65 536 envs (profiles/r02_persistent.md).  The strict check is tests/tools/multi_gpu_check.py: bit-exact vs oracle32.
+        H = 2 if shape["persistent"] else 6
         eng.reset()
         barrier()
         eng.step(H)
@@ -329,7 +334,7 @@ def main():
                 Ws = se.weights()
             # same envs, same RNG streams; the fp32 sums associate differently on 1 and N GPUs: tolerance, not identity
             err = float(np.abs(Wm - Ws).max() / max(np.abs(Ws).max(), 1e-30))
-            tol = 1e-9 if dtype == abi.F64 else 2e-4
+            tol = 1e-9 if dtype == abi.F64 else (2e-6 if shape["persistent"] else 2e-4)
             checks["single_gpu_rel_err"] = err
             checks["single_gpu_horizon_steps"] = H
             match = int(err < tol and np.isfinite(Wm).all())
