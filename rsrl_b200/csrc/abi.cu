@@ -1192,6 +1192,10 @@ int rsrl_engine_peer_attach(rsrl_engine_t* e, const uint8_t* handles, int rank, 
     }
     e->peer.rank = rank; e->peer.world = world;
     e->rank = rank; e->world = world;
+    if (!getenv("RSRL_B200_NGROUPS")) {  // CTA groups per GPU: world x groups arrivals per world-table word (measured: 8 groups at 2 GPUs, 4 at 8)
+        int ng = 32 / world;
+        e->sync.ngroups = ng > kMaxGroups ? kMaxGroups : ng < 2 ? 2 : ng;
+    }
     e->peers_attached = true;
     return RSRL_OK;
 }
