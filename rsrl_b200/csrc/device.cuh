@@ -586,7 +586,7 @@ __host__ __device__ __forceinline__ uint32_t tile_div_magic(int n_tilings) {
 // numerators of in-range states (n * (magic * T - 2^32) < 2^32 holds for n < 2^28, T <= 16); anything else divides.
 __host__ __device__ __forceinline__ int32_t tile_div(int32_t n, const TileParams& tp) {
 #ifdef __CUDA_ARCH__
-    if (n >= 0 && n < (1 << 24)) return (int32_t)__umulhi((uint32_t)n, tp.div_magic);
+    if (tp.div_magic != 0u && n >= 0 && n < (1 << 24)) return (int32_t)__umulhi((uint32_t)n, tp.div_magic);  // (one tiling: 2^32 does not fit, magic = 0)
 #endif
     return n / tp.n_tilings;
 }

@@ -580,6 +580,22 @@ def test_tile_rows_bit_exact(E, oracle, domain):
     assert np.abs(E.lfa_evaluate(cfg, W, s) - oracle.evaluate(cfg, W, s)).max() < 1e-12
 
 
+@pytest.mark.parametrize("n_tilings,tiles", [(1, 8), (3, 5), (5, 16), (7, 3), (12, 8), (16, 31)])
+def test_tile_rows_bit_exact_any_tiling_count_and_out_of_range_states(E, oracle, n_tilings, tiles):
+    """(q + offset) / n_tilings is a multiply-high by a precomputed reciprocal on the device (exact for the non-negative numerators
+    of in-range states) and a plain division otherwise: rows must equal the oracle's for every tiling count, including states far
+    outside the domain's limits (negative and huge numerators take the division path)."""
+    cfg = _tile_cfg(domain=CP, n_tilings=n_tilings, tiles_per_dim=tiles, memory_size=2048)
+    lo, hi = oracle.domain_limits(CP)
+    rng = np.random.default_rng(n_tilings)
+    s = rng.uniform(lo, hi, size=(600, 4))
+    s[:100] = rng.uniform(lo - 3 * (hi - lo), hi + 3 * (hi - lo), size=(100, 4))   # out of range, both sides
+    s[100:110] = rng.uniform(-1e5, 1e5, size=(10, 4)) * (hi - lo)                   # numerators beyond 2^24
+    s[110], s[111] = lo, hi
+    got, want = E.basis_project(cfg, s), oracle.project(cfg, s)
+    assert (got == want).all()
+
+
 @pytest.mark.parametrize("algo", [abi.SARSA, abi.QLEARNING, abi.EXPECTED_SARSA])
 def test_tile_engine_free_run_f64(E, oracle, algo):
     cfg = _tile_cfg(algo=algo, alpha=1.0)
@@ -658,6 +674,32 @@ def test_tile_handle_and_policy_entry_points(E, oracle):
         assert (e.sample(s, draw=4) == oracle.policy_sample_batch(cfg.policy, cfg.epsilon, cfg.seed, 4, 0, oracle.evaluate(cfg, W, s))).all()
         td_e, td_o = e.handle(s, a, r, ns, term, draw_idx=2), o.handle(s, a, r, ns, term, draw_idx=2)
         assert np.abs(td_e - td_o).max() < 1e-12 and np.abs(e.weights() - o.weights()).max() < 1e-11
+
+
+def test_cfg3_full_size_teacher_forced(E, oracle):
+    """BASELINE configs[2] at its full size (262 144 CartPole envs, SARSA, tile coding), dtype f32: three steps, each from the
+    device's own states and weights, against the f64 oracle.  Rows are integer work (exact); Q is a sum of <= 8 weights."""
+    cfg = _tile_cfg(n_envs=262144, dtype=abi.F32, seed=0)
+    rng = np.random.default_rng(4)
+    with E.Engine(cfg) as e:
+        o = oracle.Engine(cfg)
+        e.set_weights(rng.normal(size=(4096, 2)) * 0.1)   # (no free-running warm-up: one oracle step of 262 144 envs takes ~10 s)
+        for t in range(3):
+            o.set_states(e.states())
+            o.set_weights(e.weights())
+            q = oracle.evaluate(cfg, e.weights(), e.states())
+            safe = np.abs(q[:, 0] - q[:, 1]) > 1e-5
+            e.step(1)
+            o.step(1)
+            e.sync()
+            assert safe.mean() > 0.95
+            assert (e.actions()[safe] == o.actions()[safe]).all()
+            same = e.actions() == o.actions()
+            assert same.mean() > 0.999
+            assert np.abs(e.states()[same] - o.states()[same]).max() < 1e-12
+            scale = max(1.0, np.abs(o.td_errors()).max())
+            assert np.abs(e.td_errors()[same] - o.td_errors()[same]).max() < 4e-6 * scale
+            assert np.abs(e.weights() - o.weights()).max() < 2e-5 * max(1.0, np.abs(o.weights()).max())
 
 
 def test_cfg3_full_size_properties(E):
@@ -762,6 +804,51 @@ def test_f4tc_single_step_matches_oracle(E, oracle, domain, n, algo):
         assert (e.actions() == o.actions()).all() and (e.episode_steps() == o.episode_steps()).all()
         assert np.abs(e.states() - o.states()).max() < 1e-12                                # f64 physics
         assert np.abs(e.weights() - o.weights()).max() < 1e-6 * np.abs(o.weights()).max()
+
+
+def test_cfg4_full_size_teacher_forced(E, oracle):
+    """BASELINE configs[3] shard: 131 072 Acrobot envs, Fourier(7), ExpectedSARSA on the tcgen05 path.  Three steps, each from the
+    device's own states and weights.  Per-env outputs (actions, next states, TD errors) against the oracle on a contiguous block
+    of 1536 envs (the reference-shaped oracle needs 16 k cosines per env-step); the FULL-SIZE weight update against an independent
+    numpy contraction dW[k, a] = sum_i [a_i = a] coef_i cos(pi c_k . x^_i) over all 131 072 envs."""
+    import itertools
+    N, OFF, NB = 131072, 40000, 1536
+    cfg = _f4tc_cfg(AC, N, abi.EXPECTED_SARSA, seed=0)
+    sub = _f4tc_cfg(AC, NB, abi.EXPECTED_SARSA, seed=0, env_offset=OFF, n_envs_global=N)
+    lo, hi = oracle.domain_limits(AC)
+    coefs = np.array(sorted(itertools.product(range(8), repeat=4), reverse=True), dtype=np.float64)   # descending; the zero vector = bias slot, last
+    rng = np.random.default_rng(2)
+    with E.Engine(cfg) as e:
+        assert e.launch_shape()["f4"] >= 2   # the tensor-core path (1 = CUDA-core fourier4.cuh)
+        o = oracle.Engine(sub)
+        e.set_weights(rng.normal(size=(4096, 3)) * 0.05)
+        e.step(2)
+        o.step(2)     # same batched-step index on both sides: it is the RNG draw counter
+        for t in range(3):
+            S0, W0 = e.states(), e.weights()
+            o.set_states(S0[OFF:OFF + NB])
+            o.set_weights(W0)
+            e.step(1)
+            o.step(1)
+            e.sync()
+            blk = slice(OFF, OFF + NB)
+            same = e.actions()[blk] == o.actions()
+            assert same.mean() > 0.995                                                          # (eps-greedy: a flip needs a near tie)
+            assert np.abs(e.states()[blk][same] - o.states()[same]).max() < 1e-12               # f64 physics
+            td_o = o.td_errors()
+            assert np.abs(e.td_errors()[blk][same] - td_o[same]).max() < 1.2e-5 * max(1.0, np.abs(td_o).max())
+            # full-size update: numpy features of the FROM states, the device's own TD errors and actions
+            act, td = e.actions(), e.td_errors()
+            coef = (cfg.lr / N) * cfg.alpha * td                                                 # expected_sarsa.rs:64, MEAN scaling
+            dW = np.zeros((4096, 3))
+            xh = (S0 - lo) / (hi - lo)
+            for c0 in range(0, N, 8192):
+                phi = np.cos(np.pi * xh[c0:c0 + 8192] @ coefs.T)                                 # [chunk, 4096]
+                for a_ in range(3):
+                    m = act[c0:c0 + 8192] == a_
+                    dW[:, a_] += phi[m].T @ coef[c0:c0 + 8192][m]
+            got = e.weights() - W0
+            assert np.abs(got - dW).max() < 1e-4 * np.abs(dW).max() + 1e-9 * np.abs(W0).max()   # fp32 W rounding: 6e-8 |W|; 3xTF32 GEMM: ~1e-5 |dW|
 
 
 def test_f4tc_dw_from_zero_weights(E, oracle):
