@@ -224,7 +224,7 @@ struct rsrl_engine {
     int pmode = 0;  // MODE template value of the persistent kernel (SHARED / PER_ENV / kModeSharedTrace)
     int pgrid = 0, pblock = 0;
     size_t psmem = 0;
-    SyncArgs sync = {nullptr, 1, 1, 1, 4, 0, 0, 0u, 0, 1, 0, 0, nullptr, nullptr};
+    SyncArgs sync = {nullptr, 1, 1, 1, 4, 0, 0, 0u, 0, 1, 0, 0, 0, nullptr, nullptr};
     size_t stage_bytes = 0;
     uint32_t xepoch = 0;  // exchange epoch: counts batched steps over the engine's life, NOT reset by rsrl_engine_reset
     int pcap = 0;  // slot stride of the CTA reduce buffers
@@ -356,6 +356,7 @@ static void choose_persistent(rsrl_engine* e) {
     // first poll 400 ns after the reductions were issued: earlier polls only queue in front of them in L2 (measured, profiles/r02_persistent.md)
     e->sync.poll_delay_ns = getenv("RSRL_B200_POLL_DELAY") ? atoi(getenv("RSRL_B200_POLL_DELAY")) : 400;
     e->sync.poll_backoff_ns = getenv("RSRL_B200_POLL_BACKOFF") ? atoi(getenv("RSRL_B200_POLL_BACKOFF")) : 0;
+    e->sync.world_backoff_ns = getenv("RSRL_B200_WORLD_BACKOFF") ? atoi(getenv("RSRL_B200_WORLD_BACKOFF")) : 0;
     if (g0 > 255) g0 = 255;  // the arrival count of one step has to fit the low byte of an accumulator word
     // cluster size 4: a B200 (8 GPCs of 16-20 SMs) holds 33 such clusters = 132 CTAs at one CTA per SM, so the 65 536 envs of
     // BASELINE configs[1] still get one thread each (497 per CTA); size 8 only packs 15 clusters = 120 CTAs (547 envs per CTA:

@@ -68,6 +68,7 @@ struct SyncArgs {
     int ngroups;              // several GPUs: CTA groups per GPU (<= kMaxGroups), each with its own table and a leader that forwards its total
     int poll_delay_ns;        // pause between the reductions and the first poll / between two polls: polls that come before the last
     int poll_backoff_ns;      // partial has landed only queue in front of the reductions in L2
+    int world_backoff_ns;     // several GPUs: pause between two polls of the world table
     unsigned long long* acc;  // [2][kMaxGroups][NV][kAccStride] running fixed-point sums of the CTA partials + arrival count in the low byte (parity double-buffered)
     long long* prev;          // [2 + 2 * kMaxGroups][NV] running sums at the previous completion: world table parity 0, 1, then every group table
 };
@@ -659,7 +660,10 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                     for (int j = tid; j < NV; j += BLOCK) {
                         const unsigned long long* word = wtab + (size_t)j * AST;
                         unsigned long long w = ld_u64_sys(word);
-                        while ((w & 0xFFull) != (cnt & 0xFFull)) w = ld_u64_sys(word);
+                        while ((w & 0xFFull) != (cnt & 0xFFull)) {
+                            if (sy.world_backoff_ns > 0) __nanosleep((unsigned)sy.world_backoff_ns);  // 148 CTAs spinning on the lines the NVLink reductions land on
+                            w = ld_u64_sys(word);
+                        }
                         const long long sum = fx_running_sum(w, cnt);
                         const long long dq = fx_sext56(sum - prevs[(2 + p) * NVP8 + j]);
                         prevs[(2 + p) * NVP8 + j] = sum;
