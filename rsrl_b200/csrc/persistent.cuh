@@ -246,18 +246,6 @@ __device__ __forceinline__ void row_butterfly(R* v, int lpr) {
 template <typename R> struct Vec16;  // 16-byte shared-memory vector of R
 template <> struct Vec16<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct Vec16<double> { typedef double2 type; static constexpr int N = 2; };
-// Makes the compiler forget what it knows about the table values (no instructions): features generated from them afterwards are
-// recomputed instead of being kept in registers (and spilled) since their last use.
-__device__ __forceinline__ void launder(float& x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void launder(double& x) { asm volatile("" : "+d"(x)); }
-template <typename R, int D, int P, int BASIS>
-__device__ __forceinline__ void launder_tab(GridTables<R, D, P, BASIS>& t) {
-#pragma unroll
-    for (int d = 0; d < D; ++d)
-#pragma unroll
-        for (int j = 0; j < P; ++j) { launder(t.c[d][j]); launder(t.s[d][j]); }
-}
-
 // acc[0] += p.even * d.even, acc[1] += p.odd * d.odd over the slots of one 16-byte group, in slot order
 __device__ __forceinline__ void pair_fma(const float4& p, const float4& d, float* acc) {
     float2 a = make_float2(acc[0], acc[1]);
@@ -492,7 +480,6 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                 if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
                 if (MODE == RSRL_PER_ENV) {
                     R* Wm = static_cast<R*>(a.W);
-                    launder_tab(tab_s);  // regenerate phi(s_t) from the tables: keeping the F values of evalS alive until here spills them
                     GB::for_each(tab_s, [&](int k, R phi) {
                         const int col = k * AW + (TDPRED ? 0 : o.act);
                         if (pe_smem) {

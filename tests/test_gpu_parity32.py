@@ -189,6 +189,23 @@ def test_ragged_sizes_bit_exact(E, oracle32, n, mode):
         _exact(e, o, f"n={n}")
 
 
+@pytest.mark.parametrize("basis,order", [(abi.FOURIER, 1), (abi.FOURIER, 2), (abi.FOURIER, 3), (abi.FOURIER, 7), (abi.POLYNOMIAL, 2), (abi.POLYNOMIAL, 3)])
+@pytest.mark.parametrize("n", [700, 65536])
+def test_every_mountain_car_basis_bit_exact(E, oracle32, basis, order, n):
+    """Every instantiated MountainCar basis on the persistent kernel: odd and even orders of the paired (FMUL2 / FFMA2) feature
+    generation, odd NV (Polynomial 2: 27 values), the run-time reduce stride of the 64-feature basis, tail passes of 4 / 9 / 16 / 0 rows."""
+    cfg = _cfg(basis=basis, basis_order=order, n_envs=n, policy=abi.EPSILON_GREEDY, epsilon=0.1, lr=0.01, max_episode_steps=50, seed=order)
+    with E.Engine(cfg) as e:
+        sh = e.launch_shape()
+        assert sh["persistent"] == 1
+        o = oracle32.Engine(cfg, sh)
+        for k in (1, 79):
+            e.step(k)
+            o.step(k)
+            e.sync()
+            _exact(e, o, f"basis={basis} order={order} n={n}")
+
+
 @pytest.mark.parametrize("domain,order,algo", [(CP, 3, abi.SARSA), (AC, 2, abi.EXPECTED_SARSA), (CP, 2, abi.QLEARNING)])
 def test_d4_domains_bit_exact(E, oracle32, domain, order, algo):
     cfg = _cfg(domain=domain, basis_order=order, algo=algo, policy=abi.EPSILON_GREEDY, epsilon=0.1, n_envs=3000, lr=0.01, alpha=0.5, gamma=0.99,
