@@ -353,8 +353,9 @@ static void choose_persistent(rsrl_engine* e) {
     e->sync.fx = e->cfg.dtype == RSRL_F32 ? 1 : 0;
     e->sync.ngroups = getenv("RSRL_B200_NGROUPS") ? atoi(getenv("RSRL_B200_NGROUPS")) : kMaxGroups;  // multi-GPU: CTA groups per GPU
     if (e->sync.ngroups < 1 || e->sync.ngroups > kMaxGroups) e->sync.ngroups = kMaxGroups;
-    // first poll 400 ns after the reductions were issued: earlier polls only queue in front of them in L2 (measured, profiles/r02_persistent.md)
-    e->sync.poll_delay_ns = getenv("RSRL_B200_POLL_DELAY") ? atoi(getenv("RSRL_B200_POLL_DELAY")) : 400;
+    // first poll 200 ns after the reductions were issued (plus the ~150 ns the precompute of the next transition takes): earlier polls
+    // only queue in front of the reductions in L2 (measured, profiles/r02_persistent.md)
+    e->sync.poll_delay_ns = getenv("RSRL_B200_POLL_DELAY") ? atoi(getenv("RSRL_B200_POLL_DELAY")) : 200;
     e->sync.poll_backoff_ns = getenv("RSRL_B200_POLL_BACKOFF") ? atoi(getenv("RSRL_B200_POLL_BACKOFF")) : 0;
     e->sync.world_backoff_ns = getenv("RSRL_B200_WORLD_BACKOFF") ? atoi(getenv("RSRL_B200_WORLD_BACKOFF")) : 0;
     if (g0 > 255) g0 = 255;  // the arrival count of one step has to fit the low byte of an accumulator word

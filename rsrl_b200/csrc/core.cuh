@@ -68,11 +68,12 @@ struct CoreOut {
 // evalS evaluates Q at the from-state (it may also record phi(s) rows for the update), evalN at s'.
 // have_tab_s: tab_s already holds the tables of s (carried over from the previous step's s').
 // tab_n returns the tables of s' (valid unless the transition was terminal).
+// step_pre (optional): Dom::step_pre(s) computed by the caller ahead of time (persistent.cuh: in the shadow of the grid exchange).
 // prep(state, tab) builds the basis tables of a state (Fourier/Polynomial grid tables or tile rows).
 template <typename R, int DOM, int AW, bool EXT, class Tab, class Prep, class EvalS, class EvalN>
 __host__ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t, uint64_t g, double* s, Prep prep, EvalS evalS, EvalN evalN,
                                          Tab& tab_s, Tab& tab_n, bool have_tab_s, CoreOut<R>& o, int ext_act, double ext_reward,
-                                         bool ext_term, const double* ext_to) {
+                                         bool ext_term, const double* ext_to, const double* step_pre = nullptr) {
     using Dom = Domain<DOM>;
     constexpr int D = Dom::D;
     constexpr bool TDPRED = AW == 1;  // TD(0)/TD(lambda) state-value prediction: W is F x 1
@@ -108,7 +109,8 @@ __host__ __device__ __forceinline__ void env_core(const StepArgs& a, uint64_t t,
         reward = ext_reward;
         o.terminated = ext_term;
     } else {
-        Dom::step(s, o.act, reward, o.terminated);
+        if (Dom::kHasPre && step_pre) Dom::step_post(s, o.act, *step_pre, reward, o.terminated);  // Dom::step_pre(s) taken ahead of time
+        else Dom::step(s, o.act, reward, o.terminated);
     }
 
     // ---- D: TD error with W_t ----

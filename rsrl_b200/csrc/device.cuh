@@ -220,10 +220,17 @@ template <> struct Domain<RSRL_MOUNTAIN_CAR> {
     __host__ __device__ __forceinline__ static bool is_terminal(const double* s) { return s[0] >= 0.6; }
     __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? 0.0 : -1.0; }  // :88-92
     static constexpr bool kCheapStep = true;  // a transition costs ~100 instructions: all A candidates can be stepped ahead of time (persistent.cuh)
+    // The action-independent part of the transition (the f64 cosine: half of its instructions) can be taken ahead of time: the
+    // persistent kernel evaluates it for s_{t+1} while it waits for the grid exchange of step t.  step == step_post(step_pre).
+    static constexpr bool kHasPre = true;
+    __host__ __device__ __forceinline__ static double step_pre(const double* s) { return dmul(-0.0025, cos64(dmul(3.0, s[0]))); }
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
+        step_post(s, action, step_pre(s), reward, terminal);
+    }
+    __host__ __device__ __forceinline__ static void step_post(double* s, int action, double pre, double& reward, bool& terminal) {
         const double a = (double)(action - 1);                                        // ALL_ACTIONS = [-1, 0, 1]
-        const double dv = dadd(dmul(0.001, a), dmul(-0.0025, cos64(dmul(3.0, s[0]))));  // :58
+        const double dv = dadd(dmul(0.001, a), pre);                                  // :58
         s[1] = dclip(-0.07, dadd(s[1], dv), 0.07);                                    // :63
         s[0] = dclip(-1.2, dadd(s[0], s[1]), 0.6);                                    // :64 (uses the new v)
         terminal = s[0] >= 0.6;                                                       // :77
@@ -285,7 +292,9 @@ template <> struct Domain<RSRL_CART_POLE> {
         return s[0] <= -2.4 || s[0] >= 2.4 || s[2] <= -TWELVE_DEGREES || s[2] >= TWELVE_DEGREES;
     }
     __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? -1.0 : 0.0; }  // :23-24,103-107
-    static constexpr bool kCheapStep = false;
+    static constexpr bool kCheapStep = false, kHasPre = false;
+    __host__ __device__ __forceinline__ static double step_pre(const double*) { return 0.0; }
+    __host__ __device__ __forceinline__ static void step_post(double* s, int action, double, double& reward, bool& terminal) { step(s, action, reward, terminal); }
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double force = action == 0 ? -10.0 : 10.0;  // ALL_ACTIONS :26
@@ -323,7 +332,9 @@ template <> struct Domain<RSRL_ACROBOT> {
         return dadd(cos64(s[0]), cos64(dadd(s[0], s[1]))) < -1.0;
     }
     __host__ __device__ __forceinline__ static double reward_of(bool terminal) { return terminal ? 0.0 : -1.0; }  // :32-33,134-138
-    static constexpr bool kCheapStep = false;
+    static constexpr bool kCheapStep = false, kHasPre = false;
+    __host__ __device__ __forceinline__ static double step_pre(const double*) { return 0.0; }
+    __host__ __device__ __forceinline__ static void step_post(double* s, int action, double, double& reward, bool& terminal) { step(s, action, reward, terminal); }
     template <bool ROLLED = false>
     __host__ __device__ __forceinline__ static void step(double* s, int action, double& reward, bool& terminal) {
         const double torque = (double)(action - 1);  // ALL_ACTIONS = [-1, 0, 1] :36

@@ -387,6 +387,18 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
     }
     typename GB::Tab tab_s, tab_n;
     bool have_tab = false;  // tab_s holds the tables of s (carried from the previous step's s')
+    // The action-independent part of the next transition (MountainCar: the f64 cosine) is evaluated for s_{t+1} while the CTA waits
+    // for the grid exchange of step t: work-neutral (it is needed at step t + 1 whatever the action), two registers, no shared memory.
+    // (fp32 engines only: in the f64 cluster exchange the leaders have no idle window before their sends — measured 13.5 -> 14.7 us per step)
+    constexpr bool PRE = Dom::kHasPre && SHAREDW && sizeof(R) == 4;
+    double pre = 0.0;
+    bool have_pre = false;
+    auto precompute = [&]() {
+        if constexpr (PRE) {
+            if (resident && active) { pre = Dom::step_pre(s); have_pre = true; }
+        }
+    };
+    precompute();
 
     // LL row ownership: lanes [row * lpr, (row + 1) * lpr) own row `row` in the exchanges between leaders
     const int row = tid / lpr, rl = tid % lpr;
@@ -475,7 +487,9 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                 auto evalS = [&](const typename GB::Tab& tab, R* q) { eval(tab, q, std::integral_constant<bool, SHAREDW && !TRACE>()); };
                 auto evalN = [&](const typename GB::Tab& tab, R* q) { eval(tab, q, std::integral_constant<bool, false>()); };
                 auto prep = [](const double* st, typename GB::Tab& tb) { grid_prepare<R, Dom, P, BASIS>(st, tb); };
-                env_core<R, DOM, AW, false>(a, t, g, s, prep, evalS, evalN, tab_s, ALIAS_TAB ? tab_s : tab_n, have_tab, o, 0, 0.0, false, nullptr);
+                env_core<R, DOM, AW, false>(a, t, g, s, prep, evalS, evalN, tab_s, ALIAS_TAB ? tab_s : tab_n, have_tab, o, 0, 0.0, false, nullptr,
+                                            (PRE && have_pre) ? &pre : nullptr);
+                have_pre = false;  // (consumed: a step without a fresh precompute() evaluates it inline)
                 if (a.td) static_cast<R*>(a.td)[i] = o.residual;
                 if (o.nonfinite) atomicExch(&a.counters->nonfinite, 1);
                 if (MODE == RSRL_PER_ENV) {
@@ -588,7 +602,7 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                 for (int w = 1; w < kPersistMaxWarps; ++w) if (w < NW) acc += v[w];
                 part[j] = acc;
             }
-            if (!FX) __syncthreads();  // fp32: thread j alone reads part[j] below (reduction, poll, W update): no barrier
+            if (!FX) { __syncthreads(); precompute(); }  // fp32: thread j alone reads part[j] below (reduction, poll, W update): no barrier
             if (prof) tick(2);
             const uint32_t epoch = sy.epoch_base + (uint32_t)step + 1u;
             const int par = (int)(epoch & 1u);
@@ -616,6 +630,7 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                     if (!(fabsf(x) < kFxLimit)) { atomicExch(&a.counters->nonfinite, 1); x = 0.0f; }  // NaN / Inf / beyond the fixed-point range
                     red_add_u64_gpu(gtab + (size_t)j * AST, ((unsigned long long)fx_from_float(x) << 8) + 1ull);
                 }
+                if (!multi || b >= NG) precompute();  // (group leaders first forward their group's total)
                 if (sy.poll_delay_ns > 0 && !multi) __nanosleep((unsigned)sy.poll_delay_ns);
                 if (!multi || b < NG) {
                     const unsigned long long cnt = (unsigned long long)((G - grp + NG - 1) / NG) * k;  // CTAs grp, grp + NG, ... over k steps
@@ -641,6 +656,7 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                     }
                 }
                 if (multi) {
+                    if (b < NG) precompute();
                     if (sy.poll_delay_ns > 0) __nanosleep((unsigned)sy.poll_delay_ns);
                     const unsigned long long cnt = (unsigned long long)pe.world * (unsigned long long)NG * k;
                     const unsigned long long* wtab = reinterpret_cast<const unsigned long long*>(pe.inbox[pe.rank]) + (size_t)p * NV * AST;
@@ -659,6 +675,7 @@ __global__ void __launch_bounds__(kPersistMaxBlock, 1) persistent_kernel(const S
                 }
               } else {
                 for (int j = tid; j < NV; j += BLOCK) Wsm[(j / AW) * WS + j % AW] += part[j];
+                precompute();
               }
             } else {
             if ((G > 1 || pe.world > 1) && !(sy.debug_skip & 1)) {
