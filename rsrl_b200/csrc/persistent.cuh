@@ -7,9 +7,9 @@
 // (bit-reproducible) reduction of NV = F*A values:
 //
 //   CTA     : env threads write phi(s_t) (feature-major rows, lane = env slot: conflict-free) while
-//             they evaluate Q(s_t), and their scaled TD error per action column.  A reducer thread owns
-//             4 rows x one slot segment (one load of the TD errors feeds 4 rows), a shuffle butterfly
-//             over the segment lanes finishes the CTA partial (`part`, NV values in shared memory).
+//             they evaluate Q(s_t), and their scaled TD error per action column.  The CTA reduce is WARP-LOCAL: each warp
+//             sums the 32 slots of its own envs right after stepping them (lane = row, FFMA2 over even / odd slots), the
+//             warp partials are added in warp order by thread j after one block barrier (`part`, NV values).
 //   hop A   : (cluster, DSMEM) every member CTA stores its partial into the cluster leader's shared memory with
 //             st.async (16 bytes per thread, shared::cluster) that complete on the leader's mbarrier (complete_tx);
 //             the leader sums the partials in rank order.  No polling: the waiters sleep on the mbarrier.
@@ -28,8 +28,9 @@
 //   to the running sum it saw at the previous completion.  Data and flag share one naturally atomic 64-bit word (no
 //   fence, no 16-byte assumption), integer addition is order independent (any arrival order gives the same bits), two
 //   tables alternate by step parity so that a fast CTA's next-step contribution cannot overtake a slow reader, and the
-//   whole exchange is ONE L2 hop.  Multi-GPU: CTA 0 forwards the GPU's total to every GPU's world table through NVLink
-//   peer pointers (red.add.u64 at system scope) and every CTA polls the world table instead.
+//   whole exchange is ONE L2 hop.  Multi-GPU: the CTAs form groups with their own tables; each group leader forwards its
+//   group's total to every GPU's world table through NVLink peer pointers (red.add.u64 at system scope) and every CTA
+//   polls the world table instead.  While a CTA waits, its envs evaluate the action-independent part of the NEXT transition.
 //   Measured against the cluster exchange in profiles/r02_persistent.md.
 //
 // Every CTA of every GPU performs the same additions in the same order, so all W copies stay bit-identical;
